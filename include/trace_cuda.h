@@ -1,0 +1,197 @@
+/* trace_cuda.h — C ABI of libtrace_cuda.so, the B200 (sm_100a) backend for the
+ * ray-tracing hot path of pxl-th/Trace.jl.
+ *
+ * The reference is pure Julia and has no FFI; the seams this ABI replaces are
+ * ordinary Julia methods (citations are file:line under the reference tree):
+ *
+ *   trace_bvh_build            <- BVHAccel(primitives, max_node_primitives)   src/accel/bvh.jl:55-80 (+ _init :87-185, _unroll :187-206)
+ *   trace_scene_upload         <- Scene(lights, aggregate)                    src/Trace.jl:176-187
+ *   trace_intersect            <- intersect!(bvh|scene, ray)                  src/accel/bvh.jl:212-258, src/Trace.jl:189-191
+ *   trace_occluded             <- intersect_p(bvh|scene, ray)                 src/accel/bvh.jl:260-299, src/Trace.jl:192-194
+ *   trace_render_whitted       <- (i::SamplerIntegrator)(scene)               src/integrators/sampler.jl:12-56
+ *   trace_render_sppm          <- (i::SPPMIntegrator)(scene)                  src/integrators/sppm.jl:132-173
+ *   trace_sppm_* (stepwise)    <- the four per-iteration passes               src/integrators/sppm.jl:153-171
+ *
+ * Conventions: every function returns 0 on success and nonzero on failure
+ * (trace_last_error gives the text); no exception crosses the ABI; all
+ * pointer arguments are caller-owned and are not retained after the call
+ * returns unless the name ends in _device (then they are device pointers on
+ * the context's GPU); calls on one context must be serialised by the caller.
+ * Indices are 0-based on this side of the ABI.
+ */
+#ifndef TRACE_CUDA_H
+#define TRACE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRACE_ABI_VERSION 1
+
+/* ---- BVH node, 32 bytes (LinearBVHLeaf / LinearBVHInterior, src/accel/bvh.jl:38-48) ----
+ * interior: first child = self + 1, second child = `offset`; meta = split_axis << 30 (axis 0,1,2)
+ * leaf:     primitives offset .. offset + n - 1 in the ordered primitive list; meta = 0xC0000000 | n
+ */
+#define TRACE_NODE_LEAF 0xC0000000u
+typedef struct trace_bvh_node {
+    float bmin[3];
+    float bmax[3];
+    uint32_t offset;
+    uint32_t meta;
+} trace_bvh_node;
+
+/* ---- shapes ---- */
+enum { TRACE_PRIM_TRIANGLE = 0, TRACE_PRIM_SPHERE = 1 };
+enum { TRACE_TRI_FLIP = 1u,        /* reverse_orientation xor transform_swaps_handedness (src/shapes/Shape.jl:1-15) */
+       TRACE_TRI_HAS_NORMALS = 2u  /* mesh.normals !== nothing (src/shapes/triangle_mesh.jl:9) */ };
+
+/* Sphere (src/shapes/sphere.jl:1-25). Matrices are row-major 4x4: m = object_to_world.m,
+ * inv_m = object_to_world.inv_m (so world_to_object.m == inv_m, src/transformations.jl:12). */
+typedef struct trace_sphere {
+    float m[16];
+    float inv_m[16];
+    float radius, z_min, z_max, theta_min, theta_max, phi_max;
+    uint32_t flip;      /* reverse_orientation xor transform_swaps_handedness */
+    uint32_t pad;
+} trace_sphere;
+
+/* One entry of the BVH-ordered primitive list (bvh.primitives, src/accel/bvh.jl:51,67,100-105). */
+typedef struct trace_prim {
+    uint32_t kind;      /* TRACE_PRIM_* */
+    uint32_t index;     /* into tri_* arrays or spheres */
+    uint32_t material;  /* into materials */
+    uint32_t original;  /* index the caller wants reported back for this primitive */
+} trace_prim;
+
+/* ---- materials (src/materials/material.jl), constant textures only ---- */
+enum { TRACE_MAT_MATTE = 0, TRACE_MAT_MIRROR = 1, TRACE_MAT_GLASS = 2, TRACE_MAT_PLASTIC = 3 };
+typedef struct trace_material {
+    uint32_t kind;
+    float a[3];          /* Matte Kd | Mirror Kr | Glass Kr | Plastic Kd */
+    float b[3];          /* Glass Kt | Plastic Ks */
+    float eta;           /* Glass index */
+    float rough_u;       /* Glass u_roughness | Plastic roughness | Matte sigma */
+    float rough_v;       /* Glass v_roughness */
+    uint32_t remap;      /* remap_roughness */
+} trace_material;
+
+/* ---- lights (src/lights/point.jl, spot.jl) ---- */
+enum { TRACE_LIGHT_POINT = 0, TRACE_LIGHT_SPOT = 1 };
+typedef struct trace_light {
+    uint32_t kind;
+    float m[16];         /* light_to_world.m, row-major */
+    float inv_m[16];     /* light_to_world.inv_m (== world_to_light.m) */
+    float I[3];
+    float position[3];   /* light_to_world(Point3f(0)) */
+    float cos_total_width, cos_falloff_start;   /* spot only */
+} trace_light;
+
+typedef struct trace_scene_desc {
+    int64_t n_nodes;      const trace_bvh_node* nodes;
+    int64_t n_prims;      const trace_prim* prims;          /* BVH leaf order */
+    int64_t n_tris;       const float* tri_vertices;        /* [n_tris][3][3], world space (TriangleMesh ctor transforms them, triangle_mesh.jl:23) */
+                          const float* tri_normals;         /* [n_tris][3][3] or NULL */
+                          const uint8_t* tri_flags;         /* [n_tris] TRACE_TRI_* */
+    int64_t n_spheres;    const trace_sphere* spheres;
+    int64_t n_materials;  const trace_material* materials;
+    int64_t n_lights;     const trace_light* lights;
+} trace_scene_desc;
+
+/* ---- camera (src/camera/perspective.jl). The host builds the two matrices with the
+ * reference's literal Transformation algebra (transformations.jl:20-22) and hands them over. ---- */
+typedef struct trace_camera {
+    float raster_to_camera[16];   /* .m, row-major */
+    float camera_to_world[16];    /* .m, row-major */
+    float lens_radius, focal_distance, shutter_open, shutter_close;
+} trace_camera;
+
+/* ---- film (src/film.jl:7-62). Pixel coordinates are 1-based like the reference's. ---- */
+typedef struct trace_film_desc {
+    int32_t crop_x0, crop_y0, crop_x1, crop_y1;   /* crop_bounds, inclusive, 1-based */
+    float filter_radius[2];
+    float filter_table[256];                        /* [y][x], 16x16 (film.jl:52-56) */
+    float scale;
+} trace_film_desc;
+
+typedef struct trace_stats {
+    uint64_t rays_extend;        /* rays through closest-hit traversal */
+    uint64_t rays_shadow;        /* rays through any-hit traversal */
+    uint64_t nodes_visited;      /* only counted when option "count_nodes" is 1 */
+    uint64_t prims_tested;
+    uint64_t kernel_launches;    /* launches of this library's kernels since the last reset */
+    double   ms_extend;          /* CUDA-event time in closest-hit kernels (option "time_kernels") */
+    double   ms_shadow;
+    double   ms_total;           /* CUDA-event time of the last render / query call, device side */
+    uint64_t queue_overflows;    /* wavefront batches re-run because a ray queue overflowed */
+    uint64_t sppm_deposits;
+} trace_stats;
+
+typedef struct trace_ctx trace_ctx;
+typedef struct trace_bvh trace_bvh;
+
+/* ---- host-side BVH build, no GPU needed ---- */
+int     trace_bvh_build(const float* prim_bounds /* [n][6] = min xyz, max xyz */, int64_t n,
+                        int max_node_primitives, trace_bvh** out);
+int64_t trace_bvh_num_nodes(const trace_bvh* bvh);
+int64_t trace_bvh_num_prims(const trace_bvh* bvh);
+int     trace_bvh_copy(const trace_bvh* bvh, trace_bvh_node* nodes_out, uint32_t* prim_order_out);
+void    trace_bvh_free(trace_bvh* bvh);
+
+/* ---- context ---- */
+int         trace_abi_version(void);
+int         trace_create(trace_ctx** out, int device, void* cuda_stream /* NULL: library-owned stream */);
+void        trace_destroy(trace_ctx* ctx);
+const char* trace_last_error(const trace_ctx* ctx);
+/* options: "slab" 0 = literal reference slab test (bounds.jl:180-200), 1 = standard slab (default 0);
+ *          "batch" camera samples per wavefront batch; "count_nodes" 0/1; "time_kernels" 0/1;
+ *          "rank"/"world" shard selection for renders (tiles / photons). */
+int         trace_set_option(trace_ctx* ctx, const char* key, int64_t value);
+int         trace_get_stats(trace_ctx* ctx, trace_stats* out);
+int         trace_reset_stats(trace_ctx* ctx);
+int         trace_synchronize(trace_ctx* ctx);
+
+int trace_scene_upload(trace_ctx* ctx, const trace_scene_desc* scene);
+
+/* ---- ray queries, host buffers. o,d: [n][3]; tmax_inout: [n] (t of the hit on return, unchanged on a miss);
+ * prim_out: [n] original index + 1, 0 = miss; b0b1_out: [n][2] barycentrics (triangles) or 0; may be NULL. ---- */
+int trace_intersect(trace_ctx* ctx, const float* o, const float* d, float* tmax_inout, int64_t n,
+                    uint32_t* prim_out, float* b0b1_out);
+int trace_occluded(trace_ctx* ctx, const float* o, const float* d, const float* tmax, int64_t n,
+                   uint8_t* out);
+/* device-resident variants: rays as two float4 arrays {o.xyz, t_max}, {d.xyz, unused}; hits float4 {t, prim+1 (bits), b0, b1} */
+int trace_intersect_device(trace_ctx* ctx, const void* ray_o_tmax_device, const void* ray_d_device,
+                           int64_t n, void* hit_out_device);
+int trace_occluded_device(trace_ctx* ctx, const void* ray_o_tmax_device, const void* ray_d_device,
+                          int64_t n, void* occluded_u8_out_device);
+
+/* ---- Whitted (src/integrators/sampler.jl). film_xyzw: [crop_h][crop_w][4] = (X, Y, Z, filter_weight_sum),
+ * accumulated into (the reference never clears the film, sampler.jl:52 / film.jl:182-193). ---- */
+int trace_render_whitted(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film,
+                         int spp, int max_depth, uint64_t seed, float* film_xyzw_inout);
+int trace_render_whitted_device(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film,
+                                int spp, int max_depth, uint64_t seed, void* film_xyzw_inout_device);
+
+/* ---- SPPM (src/integrators/sppm.jl) ---- */
+typedef void (*trace_sppm_cb)(void* user, int iteration, const float* rgb /* [crop_h][crop_w][3] */);
+int trace_render_sppm(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film,
+                      float initial_radius, int max_depth, int n_iterations, int64_t photons_per_iteration,
+                      int write_frequency, uint64_t seed, trace_sppm_cb on_image, void* user,
+                      float* rgb_out /* [crop_h][crop_w][3], image after the last iteration (sppm.jl:461-472) */);
+/* stepwise form used for multi-GPU photon sharding: begin; per iteration {camera_pass; photon_pass(range);
+ * allreduce the buffer returned by trace_sppm_flux_device; update}; image; end. */
+int   trace_sppm_begin(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film,
+                       float initial_radius, int max_depth, int64_t photons_per_iteration, uint64_t seed);
+int   trace_sppm_camera_pass(trace_ctx* ctx, int iteration);
+int   trace_sppm_photon_pass(trace_ctx* ctx, int iteration, int64_t photon_begin, int64_t photon_end);
+void* trace_sppm_flux_device(trace_ctx* ctx, int64_t* n_floats /* 4 per pixel: Phi.rgb, M */);
+int   trace_sppm_update(trace_ctx* ctx);
+int   trace_sppm_image(trace_ctx* ctx, int iteration, float* rgb_out);
+int   trace_sppm_end(trace_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACE_CUDA_H */

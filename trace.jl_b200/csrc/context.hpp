@@ -1,0 +1,100 @@
+// context.hpp — host-side state of one trace_ctx (one GPU, one stream) shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "device_common.cuh"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    // grow-only device allocation
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        size_t want = need + need / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct SppmState;
+
+struct trace_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    std::string err;
+
+    // options
+    int slab = 0;                 // 0 literal reference slab test, 1 standard slab test
+    int64_t batch = 1 << 21;      // camera samples per wavefront batch
+    int count_nodes = 0;
+    int time_kernels = 0;
+    int rank = 0, world = 1;
+
+    // scene
+    bool have_scene = false;
+    DeviceScene scene{};
+    DevBuf b_nodes, b_prims, b_tnorm, b_spheres, b_materials, b_lights;
+
+    // scratch
+    DevBuf b_query[4];            // ray query staging
+    DevBuf b_queue[16];           // wavefront queues
+    DevBuf b_misc[8];
+    DevBuf b_counters;            // int counters + u64 stats block
+    int* h_flags = nullptr;       // pinned host mirror of [overflow, error]
+
+    trace_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+
+    SppmState* sppm = nullptr;
+
+    int fail(const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+        return 1;
+    }
+};
+
+#define TR_CUDA(ctx, call)                                                                  \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) return (ctx)->fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// u64 device stats block layout (ctx->b_counters, after the int counters)
+enum { ST_RAYS_EXTEND = 0, ST_RAYS_SHADOW = 1, ST_NODES = 2, ST_PRIMS = 3, ST_DEPOSITS = 4, ST_COUNT = 8 };
+static const int TR_INT_COUNTERS = 64;     // ints at the start of b_counters
+// int counter slots
+enum { IC_OVERFLOW = 60, IC_ERROR = 61 };
+
+inline int* ctx_icounters(trace_ctx* c) { return c->b_counters.as<int>(); }
+inline unsigned long long* ctx_stats64(trace_ctx* c) {
+    return reinterpret_cast<unsigned long long*>(c->b_counters.as<char>() + TR_INT_COUNTERS * sizeof(int));
+}
+
+// grid for persistent grid-stride kernels: a multiple of the SM count
+inline int persistent_grid(const trace_ctx* c, int blocks_per_sm) { return c->num_sms * blocks_per_sm; }
+
+// implemented in api.cu
+int ctx_device_film(trace_ctx* ctx, const trace_film_desc* film, DeviceFilm* out, DevBuf* table_buf);
+void ctx_device_camera(const trace_camera* cam, DeviceCamera* out);
+int ctx_pull_stats(trace_ctx* ctx);
+// implemented in whitted.cu / sppm.cu
+int whitted_render_device(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film, int spp, int max_depth,
+                          uint64_t seed, float* film_xyzw_device);
+void sppm_free(trace_ctx* ctx);

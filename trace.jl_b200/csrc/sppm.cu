@@ -1,0 +1,677 @@
+// sppm.cu — Stochastic Progressive Photon Mapping on the same wavefront stages as whitted.cu.
+//
+// Replaces src/integrators/sppm.jl:132-569: _generate_visible_sppm_points! (camera pass), _clean_grid! +
+// _populate_grid! (hash grid of visible points), _trace_photons! (photon pass with deposits), _update_pixels! and
+// _sppm_to_image.  Quirks kept: Q7 photon beta never updated, Q8 Ld not multiplied by beta, Q9 tau
+// update without vp.beta and N / radius in Float64, Q10 a visible point sits in every hashed cell its +-r box
+// overlaps (duplicates kept) and the hash is evaluated in UInt64, Q22 default photon count, Q23 visible-point rule.
+//
+// Data layout: per-pixel state as float4 arrays; the reference's per-cell linked lists become a CSR table
+// (cell_start[n_pixels+1], cell_items[]) rebuilt each iteration by count -> scan -> fill; deposits are one 128-bit
+// vector atomic (Phi.rgb, M) per accepted visible point.  The flux buffer is what multi-GPU runs all-reduce.
+#include "context.hpp"
+#include "shading.cuh"
+#include "wavefront.cuh"
+
+struct GridParams {
+    float lo[3], hi[3];
+    float max_radius;
+    int res[3];
+    int valid;
+    unsigned int total_items;
+};
+
+struct SppmLaunch {
+    DeviceScene sc;
+    DeviceCamera cam;
+    DeviceFilm film;
+    int max_depth, iteration;
+    uint64_t seed;
+    int W, H, npix;
+    long long photons_per_iteration;
+    // per-pixel state
+    float4* Ld;        // rgb
+    float4* flux;      // Phi.rgb, M
+    float4* tau_r;     // tau.rgb, radius
+    double* N;
+    float4 *vpA, *vpB, *vpC, *vpD, *vpE;   // {p, r^2} {wo, material} {ns, valid} {ss, -} {ng, -}
+    // grid
+    GridParams* grid;
+    unsigned int *cell_start, *cell_cursor, *cell_items;
+    unsigned int items_cap;
+    // queues
+    float4 *ro[2], *rd[2], *rw[2], *hits;
+    float4 *so, *sd, *sc_contrib;
+    int* counters;
+    int cap;
+    // photons
+    long long photon_begin;    // first photon index (within the iteration) of this launch
+    int n_photons;
+    const float* light_cdf;    // n_lights + 1
+    const float* light_func;   // n_lights
+    float light_func_int;
+    unsigned long long* stats;
+};
+
+// ---------------------------------------------------------------- camera pass
+__global__ void __launch_bounds__(256) k_sppm_cam_generate(SppmLaunch L) {
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+        const int px = L.film.crop_x0 + pix % L.W, py = L.film.crop_y0 + pix / L.W;
+        const uint32_t it = (uint32_t)L.iteration;
+        const float u0 = rng_uniform(L.seed, (uint32_t)pix, it, 0), u1 = rng_uniform(L.seed, (uint32_t)pix, it, 1);
+        float l0 = 0.0f, l1 = 0.0f;
+        if (L.cam.lens_radius > 0.0f) { l0 = rng_uniform(L.seed, (uint32_t)pix, it, 2); l1 = rng_uniform(L.seed, (uint32_t)pix, it, 3); }
+        float3 o, d;
+        generate_camera_ray(L.cam, (float)px + u0, (float)py + u1, l0, l1, o, d);
+        L.ro[0][pix] = f4(o, TR_INF);
+        L.rd[0][pix] = f4(d, __int_as_float(pix));
+        L.rw[0][pix] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        if (pix == 0) L.counters[1] = L.npix;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level) {
+    const int cur = (level - 1) & 1, nxt = level & 1;
+    const int n = min(L.counters[level], L.cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 h = L.hits[i];
+        const uint32_t prim1 = __float_as_uint(h.y);
+        if (prim1 == 0u) continue;
+        const float4 o4 = L.ro[cur][i], d4 = L.rd[cur][i];
+        float3 beta = xyz(L.rw[cur][i]);
+        float3 d = xyz(d4);
+        if (d.x == 0.0f) d.x = 0.0f;
+        if (d.y == 0.0f) d.y = 0.0f;
+        if (d.z == 0.0f) d.z = 0.0f;
+        const int pix = __float_as_int(d4.w);
+        const uint32_t prim = prim1 - 1u;
+        const float b2 = third_barycentric(L.sc, prim, xyz(o4), d);
+        const Interaction it = build_interaction(L.sc, prim, xyz(o4), d, h.z, h.w, b2);
+        const Frame fr = make_frame(it);
+        LobeSet lobes;
+        material_lobes(L.sc.materials[it.material], true, lobes);
+        const float3 wo = -d;
+        const uint32_t dim = 5u + 8u * (uint32_t)(level - 1), itn = (uint32_t)L.iteration;
+        // uniform_sample_one_light + estimate_direct (sppm.jl:503-554); NOT multiplied by beta (Q8)
+        {
+            const int nl = L.sc.n_lights;
+            const float ul = rng_uniform(L.seed, (uint32_t)pix, itn, dim + 0);
+            const int ln = max(1, min((int)ceilf(ul * (float)nl), nl));
+            const float light_pdf = 1.0f / (float)nl;
+            float3 wi, lpos;
+            const float3 Li = sample_li(L.sc.lights[ln - 1], it.p, wi, lpos);
+            if (!is_black3(Li)) {
+                const float3 f = bsdf_f(lobes, fr, it.wo, wi, LB_ALL & ~LB_SPECULAR) * fabsf(dot3(wi, it.ns));
+                if (!is_black3(f)) {
+                    const float3 contrib = ((f * Li) / 1.0f) / light_pdf;
+                    const float3 sdir = lpos - it.p;
+                    const int q = queue_claim(&L.counters[32 + level]);
+                    L.so[q] = f4(it.p + 1e-6f * sdir, TR_INF);
+                    L.sd[q] = f4(sdir, __int_as_float(pix));
+                    L.sc_contrib[q] = f4(contrib, 0.0f);
+                }
+            }
+        }
+        const bool is_diffuse = num_components(lobes, LB_DIFFUSE | LB_REFLECTION | LB_TRANSMISSION) > 0;
+        const bool is_glossy = num_components(lobes, LB_GLOSSY | LB_REFLECTION | LB_TRANSMISSION) > 0;
+        if (is_diffuse || (is_glossy && level == L.max_depth)) {
+            const float r = L.tau_r[pix].w;
+            L.vpA[pix] = f4(it.p, r * r);
+            L.vpB[pix] = f4(wo, __uint_as_float(it.material));
+            L.vpC[pix] = f4(fr.ns, is_black3(beta) ? 0.0f : 1.0f);
+            L.vpD[pix] = f4(fr.ss, 0.0f);
+            L.vpE[pix] = f4(fr.ng, 0.0f);
+            continue;
+        }
+        if (level == L.max_depth) continue;
+        const BSDFSample bs = bsdf_sample(lobes, fr, wo, rng_uniform(L.seed, (uint32_t)pix, itn, dim + 5),
+                                          rng_uniform(L.seed, (uint32_t)pix, itn, dim + 6), LB_ALL);
+        if (bs.pdf == 0.0f || is_black3(bs.f)) continue;
+        beta = beta * (bs.f * fabsf(dot3(bs.wi, it.ns)) / bs.pdf);
+        const float by = luminance(beta);
+        if (by < 0.25f) {
+            const float cp = fminf(1.0f, by);
+            if (rng_uniform(L.seed, (uint32_t)pix, itn, dim + 7) > cp) continue;
+            beta = beta / cp;
+        }
+        const int q = queue_claim(&L.counters[level + 1]);
+        L.ro[nxt][q] = f4(it.p + 1e-6f * bs.wi, TR_INF);
+        L.rd[nxt][q] = f4(bs.wi, __int_as_float(pix));
+        L.rw[nxt][q] = f4(beta, 0.0f);
+    }
+}
+
+// ---------------------------------------------------------------- grid build (sppm.jl:278-318)
+__device__ __forceinline__ void atomic_min_float(float* a, float v) {
+    if (v >= 0.0f) atomicMin((int*)a, __float_as_int(v)); else atomicMax((unsigned int*)a, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* a, float v) {
+    if (v >= 0.0f) atomicMax((int*)a, __float_as_int(v)); else atomicMin((unsigned int*)a, __float_as_uint(v));
+}
+
+__global__ void k_grid_reset(GridParams* g) {
+    for (int k = 0; k < 3; ++k) { g->lo[k] = TR_INF; g->hi[k] = -TR_INF; g->res[k] = 1; }
+    g->max_radius = 0.0f; g->valid = 0; g->total_items = 0;
+}
+
+__global__ void __launch_bounds__(256) k_grid_bounds(SppmLaunch L) {
+    float lo[3] = {TR_INF, TR_INF, TR_INF}, hi[3] = {-TR_INF, -TR_INF, -TR_INF}, mr = 0.0f;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+        if (L.vpC[pix].w == 0.0f) continue;                       // is_black(vp.beta)
+        const float4 A = L.vpA[pix];
+        const float r = L.tau_r[pix].w;
+        lo[0] = fminf(lo[0], A.x - r); lo[1] = fminf(lo[1], A.y - r); lo[2] = fminf(lo[2], A.z - r);   // expand(Bounds3(p), r)
+        hi[0] = fmaxf(hi[0], A.x + r); hi[1] = fmaxf(hi[1], A.y + r); hi[2] = fmaxf(hi[2], A.z + r);
+        mr = fmaxf(mr, r);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+        }
+        mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, off));
+    }
+    if ((threadIdx.x & 31) == 0 && mr > 0.0f) {
+        for (int k = 0; k < 3; ++k) { atomic_min_float(&L.grid->lo[k], lo[k]); atomic_max_float(&L.grid->hi[k], hi[k]); }
+        atomic_max_float(&L.grid->max_radius, mr);
+    }
+}
+
+__global__ void k_grid_params(GridParams* g) {                    // sppm.jl:293-301
+    if (!(g->max_radius > 0.0f)) { g->valid = 0; return; }
+    const float dx = g->hi[0] - g->lo[0], dy = g->hi[1] - g->lo[1], dz = g->hi[2] - g->lo[2];
+    const float max_diag = fmaxf(fmaxf(dx, dy), dz);
+    const long long base = (long long)floorf(max_diag / g->max_radius);
+    const float dg[3] = {dx, dy, dz};
+    for (int k = 0; k < 3; ++k) {
+        long long r = (long long)floorf((float)base * dg[k] / max_diag);
+        g->res[k] = (int)max(1ll, min(r, 1ll << 30));
+    }
+    g->valid = 1;
+}
+
+// to_grid (sppm.jl:479-495): returns in_bounds, writes the clamped cell
+__device__ __forceinline__ bool to_grid(const GridParams& g, float3 p, int cell[3]) {
+    const float o[3] = {p.x - g.lo[0], p.y - g.lo[1], p.z - g.lo[2]};          // offset(bounds, p), bounds.jl:134-143
+    const bool gx = g.hi[0] > g.lo[0], gy = g.hi[1] > g.lo[1], gz = g.hi[2] > g.lo[2];
+    const bool gg[3] = {gx, gy, gz};
+    bool in = true;
+    for (int k = 0; k < 3; ++k) {
+        float off = o[k];
+        if (gx || gy || gz) off = off / (gg[k] ? g.hi[k] - g.lo[k] : 1.0f);
+        const float f = floorf((float)g.res[k] * off);
+        // Int64(floor(...)) then 0 <= c < res
+        if (!(f >= 0.0f && f < (float)g.res[k])) in = false;
+        const float cl = fminf(fmaxf(f, 0.0f), (float)(g.res[k] - 1));
+        cell[k] = (f != f) ? 0 : (int)cl;
+    }
+    return in;
+}
+__device__ __forceinline__ unsigned int grid_hash(int x, int y, int z, unsigned int size) {    // sppm.jl:497-501, UInt64 math (Q10)
+    const unsigned long long h = ((unsigned long long)x * 73856093ull) ^ ((unsigned long long)y * 19349663ull) ^
+                                 ((unsigned long long)z * 83492791ull);
+    return (unsigned int)(h % (unsigned long long)size);
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_grid_insert(SppmLaunch L) {
+    const GridParams g = *L.grid;
+    if (!g.valid) return;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+        if (L.vpC[pix].w == 0.0f) continue;
+        const float4 A = L.vpA[pix];
+        const float r = L.tau_r[pix].w;
+        int c0[3], c1[3];
+        to_grid(g, f3(A.x - r, A.y - r, A.z - r), c0);
+        to_grid(g, f3(A.x + r, A.y + r, A.z + r), c1);
+        for (int z = c0[2]; z <= c1[2]; ++z) for (int y = c0[1]; y <= c1[1]; ++y) for (int x = c0[0]; x <= c1[0]; ++x) {
+            const unsigned int h = grid_hash(x, y, z, (unsigned int)L.npix);
+            if (!FILL) atomicAdd(&L.cell_start[h], 1u);
+            else {
+                const unsigned int slot = atomicAdd(&L.cell_cursor[h], 1u);
+                if (slot < L.items_cap) L.cell_items[slot] = (unsigned int)pix;
+            }
+        }
+    }
+}
+
+// exclusive scan of cell_start[0..n) in three small kernels (block scan, scan of block sums, add)
+#define SCAN_BLOCK 1024
+#define SCAN_ITEMS 4
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_blocks(unsigned int* data, int n, unsigned int* block_sums) {
+    __shared__ unsigned int warp_sums[32];
+    const int base = blockIdx.x * SCAN_BLOCK * SCAN_ITEMS + threadIdx.x * SCAN_ITEMS;
+    unsigned int v[SCAN_ITEMS], sum = 0;
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? data[base + k] : 0u; sum += v[k]; }
+    unsigned int incl = sum;
+    for (int off = 1; off < 32; off <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, incl, off); if ((threadIdx.x & 31) >= off) incl += t; }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned int w = warp_sums[threadIdx.x], wi = w;
+        for (int off = 1; off < 32; off <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, wi, off); if (threadIdx.x >= off) wi += t; }
+        warp_sums[threadIdx.x] = wi - w;
+        if (threadIdx.x == 31) block_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    unsigned int excl = warp_sums[threadIdx.x >> 5] + incl - sum;
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) data[base + k] = excl; excl += v[k]; }
+}
+__global__ void k_scan_sums(unsigned int* block_sums, int n_blocks, GridParams* g) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int i = 0; i < n_blocks; ++i) { unsigned int t = block_sums[i]; block_sums[i] = acc; acc += t; }
+        g->total_items = acc;
+    }
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(unsigned int* data, int n, const unsigned int* block_sums, unsigned int* cursor) {
+    const int base = blockIdx.x * SCAN_BLOCK * SCAN_ITEMS + threadIdx.x * SCAN_ITEMS;
+    const unsigned int add = block_sums[blockIdx.x];
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) { unsigned int v = data[base + k] + add; data[base + k] = v; cursor[base + k] = v; }
+}
+__global__ void k_grid_check(SppmLaunch L) {
+    if (L.grid->total_items > L.items_cap) L.counters[IC_OVERFLOW] = 1;
+    L.cell_start[L.npix] = L.grid->total_items;
+}
+
+// ---------------------------------------------------------------- photon pass (sppm.jl:320-436)
+__global__ void __launch_bounds__(256) k_photon_generate(SppmLaunch L) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L.n_photons; j += gridDim.x * blockDim.x) {
+        const unsigned long long hidx = (unsigned long long)(L.iteration - 1) * (unsigned long long)L.photons_per_iteration +
+                                        (unsigned long long)(L.photon_begin + j);
+        // light choice: sample_discrete(light_distribution, halton dim 0), sampling.jl:32-41
+        const float ls = radical_inverse(0, hidx);
+        const int nl = L.sc.n_lights;
+        int last = -1;
+        for (int k = 0; k <= nl; ++k) if (L.light_cdf[k] <= ls) last = k;
+        const int ln = min(max(last, 0), nl - 1);
+        const float light_pdf = L.light_func_int > 0.0f ? L.light_func[ln] / (L.light_func_int * (float)nl) : 0.0f;
+        const DeviceLight& light = L.sc.lights[ln];
+        const float u0 = radical_inverse(1, hidx), u1 = radical_inverse(2, hidx);
+        // sample_le (point.jl:60-69, spot.jl:46-55)
+        float3 d, le;
+        float pdf_dir;
+        const float3 I = f3(light.I[0], light.I[1], light.I[2]);
+        if (light.kind == TRACE_LIGHT_POINT) { d = uniform_sphere(u0, u1); pdf_dir = 1.0f / (4.0f * TR_PI); le = I; }
+        else {
+            d = xform_vector(light.m, uniform_cone(u0, u1, light.cos_total));
+            pdf_dir = 1.0f / (2.0f * TR_PI * (1.0f - light.cos_total));
+            le = I * spot_falloff(light, d);
+        }
+        const float pdf_pos = 1.0f;
+        if (pdf_dir == 0.0f || is_black3(le)) continue;
+        const float3 beta = (fabsf(dot3(d, d)) * le) / (light_pdf * pdf_pos * pdf_dir);      // light_normal == ray.d
+        if (is_black3(beta)) continue;
+        const int q = queue_claim(&L.counters[1]);
+        L.ro[0][q] = f4(f3(light.pos[0], light.pos[1], light.pos[2]), TR_INF);
+        L.rd[0][q] = f4(d, __int_as_float(j));
+        L.rw[0][q] = f4(beta, luminance(beta));
+    }
+}
+
+__global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
+    const int cur = (level - 1) & 1, nxt = level & 1;
+    const int n = min(L.counters[level], L.cap);
+    unsigned int deposits = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 h = L.hits[i];
+        const uint32_t prim1 = __float_as_uint(h.y);
+        if (prim1 == 0u) continue;
+        const float4 o4 = L.ro[cur][i], d4 = L.rd[cur][i], w4 = L.rw[cur][i];
+        const float3 beta = xyz(w4);
+        float3 d = xyz(d4);
+        if (d.x == 0.0f) d.x = 0.0f;
+        if (d.y == 0.0f) d.y = 0.0f;
+        if (d.z == 0.0f) d.z = 0.0f;
+        const uint32_t prim = prim1 - 1u;
+        const float b2 = third_barycentric(L.sc, prim, xyz(o4), d);
+        const Interaction it = build_interaction(L.sc, prim, xyz(o4), d, h.z, h.w, b2);
+        const float3 wo = -d;
+        if (level > 1) {
+            // deposit into every visible point of the hashed cell within its radius (sppm.jl:377-403)
+            const GridParams& g = *L.grid;
+            int cell[3];
+            if (g.valid && to_grid(g, it.p, cell)) {
+                const unsigned int hsh = grid_hash(cell[0], cell[1], cell[2], (unsigned int)L.npix);
+                const unsigned int e0 = L.cell_start[hsh], e1 = L.cell_start[hsh + 1];
+                for (unsigned int e = e0; e < e1; ++e) {
+                    const unsigned int pix = L.cell_items[e];
+                    const float4 A = L.vpA[pix];
+                    const float3 dd = xyz(A) - it.p;
+                    if (dot3(dd, dd) > A.w) continue;
+                    const float4 Bv = L.vpB[pix];
+                    Frame vf;
+                    vf.ns = xyz(L.vpC[pix]); vf.ss = xyz(L.vpD[pix]); vf.ng = xyz(L.vpE[pix]);
+                    vf.ts = cross3(vf.ns, vf.ss);
+                    LobeSet vl;
+                    material_lobes(L.sc.materials[__float_as_uint(Bv.w)], true, vl);
+                    const float3 phi = beta * bsdf_f(vl, vf, xyz(Bv), wo, LB_ALL);
+                    atomicAdd(&L.flux[pix], make_float4(phi.x, phi.y, phi.z, 1.0f));
+                    deposits++;
+                }
+            }
+        }
+        const Frame fr = make_frame(it);
+        LobeSet lobes;
+        material_lobes(L.sc.materials[it.material], true, lobes);
+        const int j = __float_as_int(d4.w);
+        const unsigned long long hidx = (unsigned long long)(L.iteration - 1) * (unsigned long long)L.photons_per_iteration +
+                                        (unsigned long long)(L.photon_begin + j);
+        const int hdim = 6 + 3 * (level - 1);
+        const BSDFSample bs = bsdf_sample(lobes, fr, wo, radical_inverse(hdim, hidx), radical_inverse(hdim + 1, hidx), LB_ALL);
+        if (is_black3(bs.f) || bs.pdf == 0.0f) continue;
+        const float3 beta_new = ((beta * bs.f) * fabsf(dot3(bs.wi, it.ns))) / bs.pdf;
+        const float q = fmaxf(0.0f, 1.0f - luminance(beta_new) / w4.w);
+        if (radical_inverse(hdim + 2, hidx) < q) continue;
+        if (level + 1 > L.max_depth) continue;
+        const int qi = queue_claim(&L.counters[level + 1]);
+        L.ro[nxt][qi] = f4(it.p + 1e-6f * bs.wi, TR_INF);
+        L.rd[nxt][qi] = f4(bs.wi, d4.w);
+        L.rw[nxt][qi] = w4;                                      // beta is NOT updated (Q7)
+    }
+    if (deposits) atomicAdd(&L.stats[ST_DEPOSITS], (unsigned long long)deposits);
+}
+
+// ---------------------------------------------------------------- per-iteration update and image (sppm.jl:438-472)
+__global__ void __launch_bounds__(256) k_sppm_update(SppmLaunch L) {
+    const float gamma = 2.0f / 3.0f;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+        const float4 fl = L.flux[pix];
+        if (fl.w > 0.0f) {
+            float4 tr = L.tau_r[pix];
+            const double N = L.N[pix];
+            const double N_new = N + (double)(gamma * fl.w);
+            const double radius_new = (double)tr.w * sqrt(N_new / (N + (double)fl.w));
+            const double ratio = radius_new / (double)tr.w;
+            const double r2 = ratio * ratio;
+            tr.x = (float)((double)(tr.x + fl.x) * r2);
+            tr.y = (float)((double)(tr.y + fl.y) * r2);
+            tr.z = (float)((double)(tr.z + fl.z) * r2);
+            tr.w = (float)radius_new;
+            L.tau_r[pix] = tr;
+            L.N[pix] = N_new;
+            L.flux[pix] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        L.vpC[pix].w = 0.0f;                                     // vp.beta = 0, vp.bsdf = nothing
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sppm_image(SppmLaunch L, int iteration, float* __restrict__ rgb) {
+    const double Np = (double)iteration * (double)L.photons_per_iteration * 3.141592653589793;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+        const float4 ld = L.Ld[pix], tr = L.tau_r[pix];
+        const double den = Np * (double)(tr.w * tr.w);
+        rgb[3 * pix + 0] = ld.x / (float)iteration + (float)((double)tr.x / den);
+        rgb[3 * pix + 1] = ld.y / (float)iteration + (float)((double)tr.y / den);
+        rgb[3 * pix + 2] = ld.z / (float)iteration + (float)((double)tr.z / den);
+    }
+}
+
+__global__ void k_sppm_init(SppmLaunch L, float r0) {
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+        L.Ld[pix] = make_float4(0, 0, 0, 0);
+        L.flux[pix] = make_float4(0, 0, 0, 0);
+        L.tau_r[pix] = make_float4(0, 0, 0, r0);
+        L.N[pix] = 0.0;
+        L.vpA[pix] = make_float4(0, 0, 0, 0); L.vpB[pix] = make_float4(0, 0, 0, 0); L.vpC[pix] = make_float4(0, 0, 0, 0);
+        L.vpD[pix] = make_float4(0, 0, 0, 0); L.vpE[pix] = make_float4(0, 0, 0, 0);
+    }
+}
+
+__global__ void k_sppm_stats(int* counters, unsigned long long* stats, int max_depth, int cap) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long e = 0, s = 0;
+        for (int l = 1; l <= max_depth; ++l) { e += min(counters[l], cap); s += counters[32 + l]; }
+        stats[ST_RAYS_EXTEND] += e; stats[ST_RAYS_SHADOW] += s;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+struct SppmState {
+    SppmLaunch L;
+    DevBuf pix[10], grid, cells[3], scan_sums, q[10], table, lights;
+    float r0;
+    int photon_cap;
+    bool active = false;
+};
+
+void sppm_free(trace_ctx* c) {
+    if (!c->sppm) return;
+    SppmState* s = c->sppm;
+    for (auto& b : s->pix) b.release();
+    for (auto& b : s->cells) b.release();
+    for (auto& b : s->q) b.release();
+    s->grid.release(); s->scan_sums.release(); s->table.release(); s->lights.release();
+    delete s;
+    c->sppm = nullptr;
+}
+
+static float host_luminance_power(const trace_ctx*, const DeviceLight& l) {       // to_Y(power(light)), sppm.jl:564-569
+    const float pi = 3.1415927f;
+    float p[3];
+    for (int k = 0; k < 3; ++k) {
+        if (l.kind == TRACE_LIGHT_POINT) p[k] = (4.0f * pi) * l.I[k];
+        else p[k] = ((l.I[k] * 2.0f) * pi) * (1.0f - 0.5f * (l.cos_falloff + l.cos_total));
+    }
+    return (0.212671f * p[0] + 0.715160f * p[1]) + 0.072169f * p[2];
+}
+
+extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const trace_film_desc* film, float r0, int max_depth,
+                                int64_t photons, uint64_t seed) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->have_scene) return c->fail("no scene uploaded");
+    if (!cam || !film) return c->fail("trace_sppm_begin: null argument");
+    if (max_depth < 1 || max_depth > 28) return c->fail("trace_sppm_begin: bad max_depth");
+    if (!(r0 > 0.0f)) return c->fail("trace_sppm_begin: bad radius");
+    if (c->scene.n_lights < 1) return c->fail("trace_sppm_begin: the scene has no lights");
+    sppm_free(c);
+    SppmState* s = new SppmState();
+    c->sppm = s;
+    SppmLaunch& L = s->L;
+    L.sc = c->scene;
+    ctx_device_camera(cam, &L.cam);
+    if (ctx_device_film(c, film, &L.film, &s->table)) return 1;
+    L.W = L.film.width; L.H = L.film.height; L.npix = L.W * L.H;
+    if (photons <= 0) photons = (int64_t)(film->crop_x1 - film->crop_x0) * (film->crop_y1 - film->crop_y0);   // area(crop_bounds), Q22
+    L.photons_per_iteration = photons;
+    L.max_depth = max_depth; L.seed = seed; L.iteration = 0;
+    s->r0 = r0;
+    const size_t np = (size_t)L.npix;
+    const size_t f4b = np * sizeof(float4);
+    for (int k = 0; k < 8; ++k) TR_CUDA(c, s->pix[k].ensure(f4b));
+    TR_CUDA(c, s->pix[8].ensure(np * sizeof(double)));
+    L.Ld = s->pix[0].as<float4>(); L.flux = s->pix[1].as<float4>(); L.tau_r = s->pix[2].as<float4>();
+    L.vpA = s->pix[3].as<float4>(); L.vpB = s->pix[4].as<float4>(); L.vpC = s->pix[5].as<float4>();
+    L.vpD = s->pix[6].as<float4>(); L.vpE = s->pix[7].as<float4>(); L.N = s->pix[8].as<double>();
+    TR_CUDA(c, s->grid.ensure(sizeof(GridParams)));
+    L.grid = s->grid.as<GridParams>();
+    L.items_cap = (unsigned int)std::min<size_t>(np * 28 + 1024, 0xFFFFFF00u);
+    TR_CUDA(c, s->cells[0].ensure((np + 1) * sizeof(unsigned int)));
+    TR_CUDA(c, s->cells[1].ensure((np + 1) * sizeof(unsigned int)));
+    TR_CUDA(c, s->cells[2].ensure((size_t)L.items_cap * sizeof(unsigned int)));
+    L.cell_start = s->cells[0].as<unsigned int>(); L.cell_cursor = s->cells[1].as<unsigned int>();
+    L.cell_items = s->cells[2].as<unsigned int>();
+    const int scan_blocks = (int)((np + 1 + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS));
+    TR_CUDA(c, s->scan_sums.ensure((size_t)scan_blocks * sizeof(unsigned int)));
+    // queues sized for max(npix, photon chunk)
+    s->photon_cap = (int)std::min<int64_t>(photons, std::max<int64_t>(c->batch * 2, 1 << 20));
+    const size_t cap = std::max<size_t>(np, (size_t)s->photon_cap);
+    L.cap = (int)cap;
+    for (int k = 0; k < 10; ++k) TR_CUDA(c, s->q[k].ensure(cap * sizeof(float4)));
+    L.ro[0] = s->q[0].as<float4>(); L.ro[1] = s->q[1].as<float4>(); L.rd[0] = s->q[2].as<float4>(); L.rd[1] = s->q[3].as<float4>();
+    L.rw[0] = s->q[4].as<float4>(); L.rw[1] = s->q[5].as<float4>(); L.hits = s->q[6].as<float4>();
+    L.so = s->q[7].as<float4>(); L.sd = s->q[8].as<float4>(); L.sc_contrib = s->q[9].as<float4>();
+    L.counters = ctx_icounters(c);
+    L.stats = ctx_stats64(c);
+    // light power distribution: Distribution1D (sampling.jl:3-30), built on the host from the uploaded lights
+    const int nl = c->scene.n_lights;
+    std::vector<DeviceLight> hl((size_t)nl);
+    TR_CUDA(c, cudaMemcpyAsync(hl.data(), c->scene.lights, (size_t)nl * sizeof(DeviceLight), cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<float> func((size_t)nl), cdf((size_t)nl + 1);
+    for (int i = 0; i < nl; ++i) func[i] = host_luminance_power(c, hl[i]);
+    cdf[0] = 0.0f;
+    for (int i = 1; i <= nl; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / (float)nl;
+    const float func_int = cdf[nl];
+    if (func_int == 0.0f) { for (int i = 1; i <= nl; ++i) cdf[i] = (float)(i + 1) / (float)nl; }
+    else { for (int i = 1; i <= nl; ++i) cdf[i] /= func_int; }
+    std::vector<float> pack(cdf);
+    pack.insert(pack.end(), func.begin(), func.end());
+    TR_CUDA(c, s->lights.ensure(pack.size() * sizeof(float)));
+    TR_CUDA(c, cudaMemcpyAsync(s->lights.p, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    L.light_cdf = s->lights.as<float>(); L.light_func = s->lights.as<float>() + nl + 1; L.light_func_int = func_int;
+    k_sppm_init<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L, r0);
+    c->stats.kernel_launches++;
+    TR_CUDA(c, cudaGetLastError());
+    s->active = true;
+    return 0;
+}
+
+static int check_flags(trace_ctx* c, const char* what) {
+    int* ic = ctx_icounters(c);
+    TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ic + IC_OVERFLOW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->h_flags[1]) { cudaMemsetAsync(ic + IC_ERROR, 0, sizeof(int), c->stream); return c->fail("%s: traversal stack overflow (> 64 pending nodes)", what); }
+    if (c->h_flags[0]) { cudaMemsetAsync(ic + IC_OVERFLOW, 0, sizeof(int), c->stream); return c->fail("%s: SPPM grid item capacity exceeded", what); }
+    return 0;
+}
+
+extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_camera_pass: call trace_sppm_begin first");
+    SppmState* s = c->sppm;
+    SppmLaunch& L = s->L;
+    L.iteration = iteration;
+    int* ic = ctx_icounters(c);
+    unsigned long long* st = ctx_stats64(c);
+    TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->stream));
+    const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
+    k_sppm_cam_generate<<<g_stream, 256, 0, c->stream>>>(L);
+    c->stats.kernel_launches++;
+    for (int level = 1; level <= L.max_depth; ++level) {
+        const int cur = (level - 1) & 1;
+        launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap, L.hits,
+                      st + ST_NODES, ic + IC_ERROR);
+        k_sppm_cam_shade<<<g_trav, 128, 0, c->stream>>>(L, level);
+        c->stats.kernel_launches++;
+        launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
+                      (const int*)(ic + 32 + level), L.cap, L.Ld, st + ST_NODES, ic + IC_ERROR);
+    }
+    k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap);
+    // hash grid of the visible points: bounds -> resolution -> count -> scan -> fill
+    const int n_cells = L.npix + 1;
+    const int scan_blocks = (n_cells + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
+    k_grid_reset<<<1, 1, 0, c->stream>>>(L.grid);
+    k_grid_bounds<<<g_stream, 256, 0, c->stream>>>(L);
+    k_grid_params<<<1, 1, 0, c->stream>>>(L.grid);
+    TR_CUDA(c, cudaMemsetAsync(L.cell_start, 0, (size_t)n_cells * sizeof(unsigned int), c->stream));
+    k_grid_insert<false><<<g_stream, 256, 0, c->stream>>>(L);
+    k_scan_blocks<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(L.cell_start, n_cells, s->scan_sums.as<unsigned int>());
+    k_scan_sums<<<1, 32, 0, c->stream>>>(s->scan_sums.as<unsigned int>(), scan_blocks, L.grid);
+    k_scan_add<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(L.cell_start, n_cells, s->scan_sums.as<unsigned int>(), L.cell_cursor);
+    k_grid_check<<<1, 1, 0, c->stream>>>(L);
+    k_grid_insert<true><<<g_stream, 256, 0, c->stream>>>(L);
+    c->stats.kernel_launches += 10;
+    TR_CUDA(c, cudaGetLastError());
+    return check_flags(c, "trace_sppm_camera_pass");
+}
+
+extern "C" int trace_sppm_photon_pass(trace_ctx* c, int iteration, int64_t begin, int64_t end) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_photon_pass: call trace_sppm_begin first");
+    SppmState* s = c->sppm;
+    SppmLaunch& L = s->L;
+    if (begin < 0 || end > L.photons_per_iteration || begin > end) return c->fail("trace_sppm_photon_pass: bad photon range");
+    L.iteration = iteration;
+    int* ic = ctx_icounters(c);
+    unsigned long long* st = ctx_stats64(c);
+    const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
+    for (int64_t b = begin; b < end; b += s->photon_cap) {
+        L.photon_begin = b;
+        L.n_photons = (int)std::min<int64_t>(s->photon_cap, end - b);
+        TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->stream));
+        k_photon_generate<<<g_stream, 256, 0, c->stream>>>(L);
+        c->stats.kernel_launches++;
+        for (int level = 1; level <= L.max_depth; ++level) {
+            const int cur = (level - 1) & 1;
+            launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap, L.hits,
+                          st + ST_NODES, ic + IC_ERROR);
+            k_photon_shade<<<g_trav, 128, 0, c->stream>>>(L, level);
+            c->stats.kernel_launches++;
+        }
+        k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap);
+        c->stats.kernel_launches++;
+    }
+    TR_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+extern "C" void* trace_sppm_flux_device(trace_ctx* c, int64_t* n_floats) {
+    if (!c || !c->sppm) return nullptr;
+    if (n_floats) *n_floats = (int64_t)c->sppm->L.npix * 4;
+    return c->sppm->L.flux;
+}
+
+extern "C" int trace_sppm_update(trace_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_update: call trace_sppm_begin first");
+    k_sppm_update<<<persistent_grid(c, 4), 256, 0, c->stream>>>(c->sppm->L);
+    c->stats.kernel_launches++;
+    TR_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int trace_sppm_image(trace_ctx* c, int iteration, float* rgb_out) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_image: call trace_sppm_begin first");
+    if (!rgb_out || iteration < 1) return c->fail("trace_sppm_image: bad argument");
+    SppmLaunch& L = c->sppm->L;
+    const size_t bytes = (size_t)L.npix * 3 * sizeof(float);
+    TR_CUDA(c, c->b_misc[6].ensure(bytes));
+    k_sppm_image<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L, iteration, c->b_misc[6].as<float>());
+    c->stats.kernel_launches++;
+    TR_CUDA(c, cudaMemcpyAsync(rgb_out, c->b_misc[6].p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    return check_flags(c, "trace_sppm_image");
+}
+
+extern "C" int trace_sppm_end(trace_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    sppm_free(c);
+    return 0;
+}
+
+extern "C" int trace_render_sppm(trace_ctx* c, const trace_camera* cam, const trace_film_desc* film, float r0, int max_depth,
+                                 int n_iterations, int64_t photons, int write_frequency, uint64_t seed, trace_sppm_cb on_image,
+                                 void* user, float* rgb_out) {
+    if (!c) return 1;
+    if (n_iterations < 1) return c->fail("trace_render_sppm: n_iterations must be >= 1");
+    if (!rgb_out) return c->fail("trace_render_sppm: null output");
+    if (trace_sppm_begin(c, cam, film, r0, max_depth, photons, seed)) return 1;
+    const int64_t P = c->sppm->L.photons_per_iteration;
+    // photon range of this rank (world > 1 needs the caller to all-reduce the flux buffer: use the stepwise API)
+    if (c->world != 1) { sppm_free(c); return c->fail("trace_render_sppm is single-GPU; use the stepwise trace_sppm_* API to shard photons"); }
+    TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int it = 1; it <= n_iterations; ++it) {
+        if (trace_sppm_camera_pass(c, it) || trace_sppm_photon_pass(c, it, 0, P) || trace_sppm_update(c)) { sppm_free(c); return 1; }
+        if (on_image && write_frequency > 0 && (it % write_frequency == 0) && it != n_iterations) {   // sppm.jl:167-171
+            if (trace_sppm_image(c, it, rgb_out)) { sppm_free(c); return 1; }
+            on_image(user, it, rgb_out);
+        }
+    }
+    TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    if (trace_sppm_image(c, n_iterations, rgb_out)) { sppm_free(c); return 1; }
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->stats.ms_total = ms;
+    if (on_image) on_image(user, n_iterations, rgb_out);
+    return trace_sppm_end(c);
+}

@@ -1,0 +1,220 @@
+// traverse.cuh — closest-hit / any-hit BVH traversal and the two shape tests, one thread per ray.
+//
+// Behavioural spec (what must match the reference bit for bit):
+//   ray preparation  src/ray.jl:25-29, src/accel/bvh.jl:217-219, src/bounds.jl:169-175
+//   slab test        src/bounds.jl:180-200   (SLAB = 0 literal, incl. the loose y far bound; SLAB = 1 standard)
+//   traversal order  src/accel/bvh.jl:221-257 / 266-298  (near child by sign of d[split_axis], far child pushed)
+//   triangle         src/shapes/triangle_mesh.jl:187-218, 245-273 (watertight shear test, FP64 only if ALL edges are 0)
+//   sphere           src/shapes/sphere.jl:39-75, 125-191
+// Layout: 32-byte nodes fetched as two 128-bit loads, 48-byte primitive records as three; a 64-entry per-thread stack
+// (the reference's `zeros(Int32, 64)`), which the compiler keeps in local memory (L1-resident near its top).
+#pragma once
+#include "device_common.cuh"
+
+struct RayPrep {            // quantities that depend on the ray only
+    float3 o, d, inv;
+    bool nx, ny, nz;
+    int kz;                 // permutation of the triangle test
+    float ox, oy, oz;       // o permuted
+    float Sx, Sy, Sz;       // shear
+};
+
+__device__ __forceinline__ RayPrep prepare_ray(float3 o, float3 d) {
+    RayPrep r;
+    // check_direction!: -0.0 -> +0.0 (x ≈ 0f0 is x == 0)
+    if (d.x == 0.0f) d.x = 0.0f;
+    if (d.y == 0.0f) d.y = 0.0f;
+    if (d.z == 0.0f) d.z = 0.0f;
+    r.o = o; r.d = d;
+    r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.nx = d.x < 0.0f; r.ny = d.y < 0.0f; r.nz = d.z < 0.0f;
+    // _to_ray_coordinate_space: kz = first argmax |d|
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int kz = 0; float am = ax;
+    if (ay > am) { kz = 1; am = ay; }
+    if (az > am) { kz = 2; }
+    r.kz = kz;
+    float dx, dy, dz;
+    if (kz == 0)      { dx = d.y; dy = d.z; dz = d.x; r.ox = o.y; r.oy = o.z; r.oz = o.x; }
+    else if (kz == 1) { dx = d.z; dy = d.x; dz = d.y; r.ox = o.z; r.oy = o.x; r.oz = o.y; }
+    else              { dx = d.x; dy = d.y; dz = d.z; r.ox = o.x; r.oy = o.y; r.oz = o.z; }
+    float denom = 1.0f / dz;
+    r.Sx = -dx * denom; r.Sy = -dy * denom; r.Sz = denom;
+    return r;
+}
+
+template <int SLAB>
+__device__ __forceinline__ bool slab_test(const float4 n0, const float4 n1, const RayPrep& r, float tmax) {
+    // bmin = (n0.x, n0.y, n0.z), bmax = (n0.w, n1.x, n1.y)
+    float tx_min = ((r.nx ? n0.w : n0.x) - r.o.x) * r.inv.x;
+    float tx_max = ((r.nx ? n0.x : n0.w) - r.o.x) * r.inv.x;
+    float ty_min = ((r.ny ? n1.x : n0.y) - r.o.y) * r.inv.y;
+    float ty_max = ((r.ny ? n0.y : n1.x) - r.o.y) * r.inv.y;
+    if (tx_min > ty_max || ty_min > tx_max) return false;
+    if (ty_min > tx_min) tx_min = ty_min;
+    if (SLAB == 0) { if (ty_max > tx_max) tx_max = ty_max; }     // bounds.jl:191 keeps the larger (Q26)
+    else           { if (ty_max < tx_max) tx_max = ty_max; }
+    float tz_min = ((r.nz ? n1.y : n0.z) - r.o.z) * r.inv.z;
+    float tz_max = ((r.nz ? n0.z : n1.y) - r.o.z) * r.inv.z;
+    if (tx_min > tz_max || tz_min > tx_max) return false;
+    if (tz_min > tx_min) tx_min = tz_min;
+    if (tz_max < tx_max) tx_max = tz_max;
+    return tx_min < tmax && tx_max > 0.0f;
+}
+
+// Watertight triangle test. a, b, c are the primitive record's float4s (xyz = vertices).
+__device__ __forceinline__ bool triangle_test(const float4 a, const float4 b, const float4 c, const RayPrep& r, float tmax,
+                                              float& t_hit, float& b0, float& b1, float& b2) {
+    float X0, Y0, Z0, X1, Y1, Z1, X2, Y2, Z2;
+    {
+        float qx = a.x - r.o.x, qy = a.y - r.o.y, qz = a.z - r.o.z;     // (v - o), then permuted
+        float px, py, pz;
+        if (r.kz == 0) { px = qy; py = qz; pz = qx; } else if (r.kz == 1) { px = qz; py = qx; pz = qy; } else { px = qx; py = qy; pz = qz; }
+        X0 = px + r.Sx * pz; Y0 = py + r.Sy * pz; Z0 = pz + 0.0f;
+    }
+    {
+        float qx = b.x - r.o.x, qy = b.y - r.o.y, qz = b.z - r.o.z;
+        float px, py, pz;
+        if (r.kz == 0) { px = qy; py = qz; pz = qx; } else if (r.kz == 1) { px = qz; py = qx; pz = qy; } else { px = qx; py = qy; pz = qz; }
+        X1 = px + r.Sx * pz; Y1 = py + r.Sy * pz; Z1 = pz + 0.0f;
+    }
+    {
+        float qx = c.x - r.o.x, qy = c.y - r.o.y, qz = c.z - r.o.z;
+        float px, py, pz;
+        if (r.kz == 0) { px = qy; py = qz; pz = qx; } else if (r.kz == 1) { px = qz; py = qx; pz = qy; } else { px = qx; py = qy; pz = qz; }
+        X2 = px + r.Sx * pz; Y2 = py + r.Sy * pz; Z2 = pz + 0.0f;
+    }
+    float e0 = X1 * Y2 - Y1 * X2;
+    float e1 = X2 * Y0 - Y2 * X0;
+    float e2 = X0 * Y1 - Y0 * X1;
+    if (e0 == 0.0f && e1 == 0.0f && e2 == 0.0f) {
+        e0 = (float)((double)X1 * (double)Y2 - (double)Y1 * (double)X2);
+        e1 = (float)((double)X2 * (double)Y0 - (double)Y2 * (double)X0);
+        e2 = (float)((double)X0 * (double)Y1 - (double)Y0 * (double)X1);
+    }
+    if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+    float det = (e0 + e1) + e2;
+    if (det == 0.0f) return false;
+    float ts = ((e0 * Z0) * r.Sz + (e1 * Z1) * r.Sz) + (e2 * Z2) * r.Sz;
+    if (det < 0.0f && (ts >= 0.0f || ts < tmax * det)) return false;
+    if (det > 0.0f && (ts <= 0.0f || ts > tmax * det)) return false;
+    float inv_det = 1.0f / det;
+    b0 = e0 * inv_det; b1 = e1 * inv_det; b2 = e2 * inv_det;
+    t_hit = ts * inv_det;
+    return true;
+}
+
+struct SphereHitInfo { float t; float3 p; float phi; };
+
+__device__ __forceinline__ float3 sphere_refine(float3 p, float radius) {
+    float f = radius / length3(f3s(0.0f) - p);
+    p = p * f;
+    if (p.x == 0.0f && p.y == 0.0f) p = f3(1e-6f * radius, p.y, p.z);
+    return p;
+}
+__device__ __forceinline__ float sphere_phi(float3 p) {
+    float phi = atan2f(p.y, p.x);
+    if (phi < 0.0f) phi += 2.0f * TR_PI;
+    return phi;
+}
+__device__ __forceinline__ bool sphere_clipped(const DeviceSphere& s, float3 p, float phi) {
+    return (s.z_min > -s.radius && p.z < s.z_min) || (s.z_max < s.radius && p.z > s.z_max) || phi > s.phi_max;
+}
+static __device__ __noinline__ bool sphere_test(const DeviceSphere& s, float3 ro, float3 rd, float tmax, SphereHitInfo& h) {
+    float3 o = xform_point(s.inv_m, ro);
+    float3 d = xform_vector(s.inv_m, rd);
+    float nd = length3(d), no = length3(o);
+    float a = nd * nd;
+    float b = dot3(2.0f * o, d);
+    float c = no * no - s.radius * s.radius;
+    float disc = b * b - (4.0f * a) * c;
+    if (disc < 0.0f) return false;
+    float rdisc = sqrtf(disc);
+    float q = -0.5f * (b + (b < 0.0f ? -rdisc : rdisc));
+    float t0 = q / a, t1 = c / q;
+    if (t0 > t1) { float tmp = t0; t0 = t1; t1 = tmp; }
+    if (t0 > tmax || t1 < 0.0f) return false;
+    if (t0 < 0.0f) t0 = t1;                                   // no t_max re-check (Q12)
+    h.t = t0;
+    h.p = sphere_refine(o + d * t0, s.radius);
+    h.phi = sphere_phi(h.p);
+    if (sphere_clipped(s, h.p, h.phi)) {
+        h.t = t1;
+        h.p = sphere_refine(o + d * t1, s.radius);
+        h.phi = sphere_phi(h.p);
+        if (sphere_clipped(s, h.p, h.phi)) return false;
+    }
+    return true;
+}
+
+#define TR_PRIM_SPHERE_BIT 0x80000000u
+#define TR_PRIM_DEGENERATE_BIT 0x40000000u
+#define TR_STACK_SIZE 64
+
+struct HitRecord {
+    uint32_t prim;      // BVH-ordered primitive index + 1, 0 = miss
+    float t, b0, b1;
+};
+
+// Returns true when something was hit. ANY: stops at the first accepted primitive (intersect_p).
+template <int SLAB, bool ANY, bool COUNT>
+__device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3 d, float tmax, HitRecord& out,
+                                         unsigned long long* counters, int* error_flag) {
+    out.prim = 0; out.t = tmax; out.b0 = 0.0f; out.b1 = 0.0f;
+    if (sc.n_nodes == 0) return false;
+    const RayPrep r = prepare_ray(o, d);
+    uint32_t stack[TR_STACK_SIZE];
+    int sp = 0;
+    uint32_t cur = 0;
+    unsigned n_nodes = 0, n_prims = 0;
+    bool found = false;
+    for (;;) {
+        const float4 n0 = __ldg(&sc.nodes[2 * cur]);
+        const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
+        if (COUNT) n_nodes++;
+        bool descend = false;
+        if (slab_test<SLAB>(n0, n1, r, tmax)) {
+            const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
+            const uint32_t count = meta & 0x3FFFFFFFu;
+            if ((meta >> 30) == 3u) {     // leaf (a zero-primitive leaf has invalid bounds and never gets here, Q16/Q17)
+                for (uint32_t i = 0; i < count; ++i) {
+                    const uint32_t pi = offset + i;
+                    const float4 a = __ldg(&sc.prims[3 * pi]);
+                    const uint32_t tag = __float_as_uint(a.w);
+                    if (COUNT) n_prims++;
+                    if (tag == 0u) {
+                        const float4 b = __ldg(&sc.prims[3 * pi + 1]);
+                        const float4 c = __ldg(&sc.prims[3 * pi + 2]);
+                        float t, b0, b1, b2;
+                        if (triangle_test(a, b, c, r, tmax, t, b0, b1, b2)) {
+                            if (ANY) { found = true; goto done; }
+                            tmax = t; found = true;
+                            out.prim = pi + 1; out.t = t; out.b0 = b0; out.b1 = b1;
+                        }
+                    } else if (tag & TR_PRIM_SPHERE_BIT) {
+                        SphereHitInfo sh;
+                        if (sphere_test(sc.spheres[tag & 0x3FFFFFFFu], r.o, r.d, tmax, sh)) {
+                            if (ANY) { found = true; goto done; }
+                            tmax = sh.t; found = true;
+                            out.prim = pi + 1; out.t = sh.t; out.b0 = 0.0f; out.b1 = 0.0f;
+                        }
+                    }   // degenerate triangles (is_degenerate, triangle_mesh.jl:65-68) never hit
+                }
+            } else {
+                const uint32_t axis = meta >> 30;
+                const bool neg = axis == 0 ? r.nx : (axis == 1 ? r.ny : r.nz);
+                if (sp >= TR_STACK_SIZE) { if (error_flag) *error_flag = 1; goto done; }
+                if (neg) { stack[sp++] = cur + 1; cur = offset; }
+                else     { stack[sp++] = offset; cur = cur + 1; }
+                descend = true;
+            }
+        }
+        if (!descend) {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+done:
+    if (COUNT && counters) { atomicAdd(&counters[0], (unsigned long long)n_nodes); atomicAdd(&counters[1], (unsigned long long)n_prims); }
+    return found;
+}

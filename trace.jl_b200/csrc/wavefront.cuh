@@ -1,0 +1,61 @@
+// wavefront.cuh — the two traversal stages shared by the Whitted and SPPM wavefronts: `extend` (closest hit over a ray
+// queue) and `shadow` (any hit over a shadow queue, fused with the accumulate: an unoccluded ray adds its
+// contribution to the accumulator slot it names).  Queue sizes live in device memory, so the kernels are launched
+// as persistent grid-stride grids (a multiple of the SM count) and no host round trip sits between stages.
+#pragma once
+#include "context.hpp"
+#include "shading.cuh"
+
+template <int SLAB, bool COUNT>
+__global__ void __launch_bounds__(128) k_wh_extend(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
+                                                   const int* __restrict__ count, int cap, float4* __restrict__ hits,
+                                                   unsigned long long* counters, int* error_flag) {
+    const int n = min(*count, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o = ro[i], d = rd[i];
+        HitRecord h;
+        // closest hit; the third barycentric is rebuilt exactly in the shade stage from the winning triangle
+        traverse<SLAB, false, COUNT>(sc, xyz(o), xyz(d), o.w, h, counters, error_flag);
+        hits[i] = make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1);
+    }
+}
+
+template <int SLAB, bool COUNT>
+__global__ void __launch_bounds__(128) k_wh_shadow(DeviceScene sc, const float4* __restrict__ so, const float4* __restrict__ sd,
+                                                   const float4* __restrict__ contrib, const int* __restrict__ count, int cap,
+                                                   float4* __restrict__ accum, unsigned long long* counters, int* error_flag) {
+    const int n = min(*count, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o = so[i], d = sd[i];
+        HitRecord h;
+        if (!traverse<SLAB, true, COUNT>(sc, xyz(o), xyz(d), o.w, h, counters, error_flag)) {
+            const float4 c = contrib[i];
+            atomicAdd(&accum[__float_as_int(d.w)], make_float4(c.x, c.y, c.z, 0.0f));   // 128-bit vector atomic (sm_90+)
+        }
+    }
+}
+
+// exact third barycentric of the winning triangle: e2 * inv_det of the same edge functions (pure function of ray + triangle)
+__device__ __forceinline__ float third_barycentric(const DeviceScene& sc, uint32_t prim, float3 o, float3 d) {
+    const float4 A = __ldg(&sc.prims[3 * prim]);
+    if (__float_as_uint(A.w) & TR_PRIM_SPHERE_BIT) return 0.0f;
+    const float4 B = __ldg(&sc.prims[3 * prim + 1]), C = __ldg(&sc.prims[3 * prim + 2]);
+    const RayPrep r = prepare_ray(o, d);
+    float t, b0, b1, b2 = 0.0f;
+    triangle_test(A, B, C, r, TR_INF, t, b0, b1, b2);
+    return b2;
+}
+
+template <class... Args>
+static void launch_extend(trace_ctx* c, int grid, Args... args) {
+    if (c->slab == 0) { if (c->count_nodes) k_wh_extend<0, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_extend<0, false><<<grid, 128, 0, c->stream>>>(args...); }
+    else              { if (c->count_nodes) k_wh_extend<1, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_extend<1, false><<<grid, 128, 0, c->stream>>>(args...); }
+    c->stats.kernel_launches++;
+}
+template <class... Args>
+static void launch_shadow(trace_ctx* c, int grid, Args... args) {
+    if (c->slab == 0) { if (c->count_nodes) k_wh_shadow<0, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_shadow<0, false><<<grid, 128, 0, c->stream>>>(args...); }
+    else              { if (c->count_nodes) k_wh_shadow<1, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_shadow<1, false><<<grid, 128, 0, c->stream>>>(args...); }
+    c->stats.kernel_launches++;
+}
+
