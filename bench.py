@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the ray-tracing hot path (BASELINE.json: "Mrays/sec (closest-hit + shadow)").
+
+A step is one pass of the hot path over one batch of synthetic input: one full Whitted render (depth 5, 16 spp,
+1920x1080) of the synthetic ~1M-triangle "tess-1M" scene (BASELINE.json configs[2]) — the
+configuration the north_star's throughput target is quoted on.  value = (rays through closest-hit traversal + rays
+through any-hit traversal) / time, whole job, scene and film resident in HBM.  e2e = the same metric through the
+host-buffer C ABI call (trace_render_whitted: film H2D + D2H inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload tess-1M|tess-small]
+N > 1: launched by torch.distributed.run, one rank per GPU, scene replicated, 16x16 sample tiles dealt round-robin,
+one NCCL reduce of the film per step (strong scaling: the image is fixed).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene kwargs, spp, depth)
+    "tess-1M": (dict(cells=600, stacks=266, slices=264, res=(1920, 1080), window=((-50.0, -28.125), (50.0, 28.125))), 16, 5),
+    "tess-small": (dict(cells=64, stacks=34, slices=32, res=(480, 270), window=((-50.0, -28.125), (50.0, 28.125))), 4, 5),
+}
+METRIC = "Mrays/sec (closest-hit + shadow)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(T, workload):
+    kw, spp, depth = WORKLOADS[workload]
+    scene, camera, _ = T.scenes.tessellated(**kw)
+    return scene, camera, spp, depth
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the C++ restatement, oracle/ — Julia is
+    not available) with all host threads, on a bounded sample (a strided subset of the 16x16 tiles) of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import trace_jl_b200 as T
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    scene, camera, spp, depth = build_scene(T, args.workload)
+    osc = oracle_lib.OracleScene(scene.flatten())
+    cam, fd = camera.pod(), camera.film.desc()
+    cores = os.cpu_count() or 1
+    film = np.zeros_like(camera.film.pixels)
+    from trace_jl_b200.distributed import n_sample_tiles
+    total_tiles = n_sample_tiles(camera.film)
+    # calibrate: ~4 s per step
+    t0 = time.time(); cnt = osc.render_whitted(cam, fd, spp, depth, 1, film, max_tiles=max(cores, 16), threads=cores); dt = time.time() - t0
+    rate = (int(cnt[0]) + int(cnt[1])) / max(dt, 1e-6)
+    tiles = int(min(total_tiles, max(cores, 16) * max(1.0, args.ref_seconds / max(dt, 1e-3))))
+    times, rays = [], []
+    for i in range(args.warmup + args.steps):
+        film[:] = 0
+        t0 = time.time(); cnt = osc.render_whitted(cam, fd, spp, depth, 1 + i, film, max_tiles=tiles, threads=cores); dt = time.time() - t0
+        if i >= args.warmup:
+            times.append(dt); rays.append(int(cnt[0]) + int(cnt[1]))
+    value = sum(rays) / sum(times) / 1e6
+    sample = f"{tiles} of {total_tiles} 16x16 sample tiles (strided over the image) per step, {spp} spp, depth {depth}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"whitted-{args.workload}", "spp": spp, "max_depth": depth,
+                   "resolution": list(WORKLOADS[args.workload][0]["res"]), "triangles": int(scene.aggregate.n_primitives)},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated reference (C++ oracle), not Trace.jl itself: no Julia in this image"}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="tess-1M", choices=sorted(WORKLOADS))
+    ap.add_argument("--slab", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--ref-seconds", type=float, default=4.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sppm", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import trace_jl_b200 as T
+    from trace_jl_b200 import distributed as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = T.Context(local, stream=stream)
+    ctx.set_option("slab", args.slab)
+    if args.batch:
+        ctx.set_option("batch", args.batch)
+
+    scene, camera, spp, depth = build_scene(T, args.workload)
+    flat = ctx.upload(scene)
+    H, W = camera.film.pixels.shape[:2]
+    film_dev = torch.zeros((H, W, 4), dtype=torch.float32, device=f"cuda:{local}")
+    film_bytes = film_dev.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        film_dev.zero_()
+        D.render_whitted_sharded(ctx, scene, camera, spp, depth, 1000 + i, film_dev, rank, world)
+
+    # ---- device-resident timing: W warm-up steps, then exactly K steps between barriers; max over ranks
+    ctx.set_option("time_kernels", 1)
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ctx.reset_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local}")
+    st = ctx.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    rays = torch.tensor([float(st["rays_extend"]), float(st["rays_shadow"]), float(st["kernel_launches"])], device=f"cuda:{local}",
+                        dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    ms_total = float(ms.item())
+    total_rays = float(rays[0] + rays[1])
+    value = total_rays / (ms_total * 1e-3) / 1e6
+    launches = int(rays[2].item())
+
+    # ---- roofline of the dominant kernel (closest-hit `extend`): algorithmic bytes / CUDA-event launch time
+    ext_ms, ext_n = st["ms_extend"], max(1, st["extend_launches"])
+    ctx.set_option("time_kernels", 0)
+    ctx.set_option("count_nodes", 1)
+    ctx.reset_stats()
+    step(10_000)                                    # instrumented pass (not timed): nodes / primitives per ray
+    torch.cuda.synchronize()
+    sc = ctx.stats()
+    ctx.set_option("count_nodes", 0)
+    n_rays_cnt = max(1, sc["rays_extend"] + sc["rays_shadow"])
+    nodes_per_ray = sc["nodes_visited"] / n_rays_cnt
+    prims_per_ray = sc["prims_tested"] / n_rays_cnt
+    bytes_per_ray = 48.0 + 32.0 * nodes_per_ray + 48.0 * prims_per_ray
+    ext_rays = st["rays_extend"]
+    achieved = (ext_rays * bytes_per_ray) / max(1e-9, ext_ms * 1e-3) / 1e9
+    peak, peak_kind = load_peaks()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "k_wh_extend", "peak_source": f"of {peak_kind}", "avg_launch_ms": ext_ms / ext_n,
+                "launches_timed": int(ext_n), "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
+                "prims_per_ray": prims_per_ray, "extend_Mrays_per_s": ext_rays / max(1e-9, ext_ms * 1e-3) / 1e6,
+                "extend_share_of_step": ext_ms / max(1e-9, ms_total) if world == 1 else None,
+                "note": "traversal is L1/L2-latency bound: algorithmic bytes are mostly cache hits, not HBM traffic"}
+    if os.path.exists(os.path.join(ROOT, "profiles", "extend_traffic.json")):
+        try:
+            roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "extend_traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- e2e: the reference-facing C ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
+    host_film = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
+    cam_pod, fd = camera.pod(), camera.film.desc()
+
+    def e2e_step(i):
+        if world == 1:
+            ctx.check(ctx.lib.trace_render_whitted(ctx.h, C.byref(cam_pod), C.byref(fd), spp, depth, C.c_uint64(2000 + i),
+                                                   C.c_void_p(host_film.data_ptr())))
+        else:
+            film_dev.copy_(host_film, non_blocking=True)
+            D.render_whitted_sharded(ctx, scene, camera, spp, depth, 2000 + i, film_dev, rank, world)
+            if rank == 0:
+                host_film.copy_(film_dev, non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_step(0)
+    barrier()
+    ctx.reset_stats()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        host_film.zero_()
+        e2e_step(1 + i)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    st2 = ctx.stats()
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=f"cuda:{local}")
+    rays2 = torch.tensor([float(st2["rays_extend"] + st2["rays_shadow"])], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays2, op=dist.ReduceOp.SUM)
+    e2e_value = float(rays2.item()) / (float(ms2.item()) * 1e-3) / 1e6
+    e2e = {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(film_bytes + C.sizeof(cam_pod) + C.sizeof(fd)),
+           "d2h_bytes_per_step": int(film_bytes), "ms_per_step": float(ms2.item()) / args.steps}
+
+    # ---- secondary metric: SPPM iterations/s on docs/code/spheres.jl ("shadows", 1024^2, depth 5), photons sharded
+    sppm = None
+    if not args.no_sppm:
+        s_scene, s_cam, kw = T.scenes.shadows(resolution=1024)
+        sess = D.SPPMSession(ctx, s_scene, s_cam, kw["initial_search_radius"], kw["max_depth"], -1, 0x5EED0001, rank, world)
+        for _ in range(3):
+            sess.step()
+        barrier()
+        n_it = 10
+        e0.record()
+        for _ in range(n_it):
+            sess.step()
+        e1.record()
+        barrier()
+        ms3 = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        sppm = {"metric": "SPPM iterations/sec", "value": n_it / (float(ms3.item()) * 1e-3), "unit": "it/s",
+                "config": {"workload": "sppm-shadows-1024", "photons_per_iteration": sess.photons, "max_depth": kw["max_depth"]}}
+        sess.close()
+        ctx.upload(scene)
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample of the same workload
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        osc = oracle_lib.OracleScene(flat)
+        cores = os.cpu_count() or 1
+        tmp = np.zeros_like(camera.film.pixels)
+        total_tiles = D.n_sample_tiles(camera.film)
+        tiles = max(cores, 16)
+        t0 = time.time(); cnt = osc.render_whitted(cam_pod, fd, spp, depth, 1, tmp, max_tiles=tiles, threads=cores); dt = time.time() - t0
+        tiles2 = int(min(total_tiles, tiles * max(1.0, 12.0 / max(dt, 1e-3))))
+        t0 = time.time(); cnt = osc.render_whitted(cam_pod, fd, spp, depth, 1, tmp, max_tiles=tiles2, threads=cores); dt = time.time() - t0
+        cpu_baseline = {"value": (int(cnt[0]) + int(cnt[1])) / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                        "sample": f"{tiles2} of {total_tiles} 16x16 sample tiles (strided over the image), {spp} spp, depth {depth}, {dt:.1f} s",
+                        "note": "restated reference (C++ oracle, std::thread over tiles), not Trace.jl itself"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"whitted-{args.workload}", "spp": spp, "max_depth": depth,
+                          "resolution": list(WORKLOADS[args.workload][0]["res"]), "triangles": int(scene.aggregate.n_primitives),
+                          "bvh_nodes": int(len(flat.nodes)), "slab_test": "literal" if args.slab == 0 else "standard",
+                          "parallelism": f"tiles-rr{world}", "l2_policy": "inputs larger than L2 (ray queues + BVH > 126 MB per step)",
+                          "rays_per_step": total_rays / args.steps},
+               "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+               "sppm": sppm}
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

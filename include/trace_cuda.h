@@ -127,6 +127,8 @@ typedef struct trace_stats {
     double   ms_total;           /* CUDA-event time of the last render / query call, device side */
     uint64_t queue_overflows;    /* wavefront batches re-run because a ray queue overflowed */
     uint64_t sppm_deposits;
+    uint64_t extend_launches;    /* closest-hit kernel launches timed into ms_extend */
+    uint64_t shadow_launches;    /* any-hit kernel launches timed into ms_shadow */
 } trace_stats;
 
 typedef struct trace_ctx trace_ctx;

@@ -115,9 +115,24 @@ static RGB whitted_li(const Scene& s, Ray ray, int depth, int max_depth, RayCoun
 
 using namespace ref;
 
+static int render_whitted_impl(const ref_scene* rs, const trace_camera* cam, const trace_film_desc* film, int spp,
+                               int max_depth, uint64_t seed, float* film_xyzw, int n_threads, int64_t max_tiles,
+                               uint64_t* ray_counters, const int64_t* tile_list, int64_t n_tile_list);
+
 extern "C" int ref_render_whitted(const ref_scene* rs, const trace_camera* cam, const trace_film_desc* film, int spp,
                                   int max_depth, uint64_t seed, float* film_xyzw, int n_threads, int64_t max_tiles,
                                   uint64_t* ray_counters) {
+    return render_whitted_impl(rs, cam, film, spp, max_depth, seed, film_xyzw, n_threads, max_tiles, ray_counters, nullptr, -1);
+}
+// explicit tile list (k = ty * n_tiles_x + tx), single thread: used to check the multi-GPU tile partition on CPU
+extern "C" int ref_render_whitted_tiles(const ref_scene* rs, const trace_camera* cam, const trace_film_desc* film, int spp,
+                                        int max_depth, uint64_t seed, float* film_xyzw, const int64_t* tiles, int64_t n_tiles) {
+    return render_whitted_impl(rs, cam, film, spp, max_depth, seed, film_xyzw, 1, 0, nullptr, tiles, n_tiles);
+}
+
+static int render_whitted_impl(const ref_scene* rs, const trace_camera* cam, const trace_film_desc* film, int spp,
+                               int max_depth, uint64_t seed, float* film_xyzw, int n_threads, int64_t max_tiles,
+                               uint64_t* ray_counters, const int64_t* tile_list, int64_t n_tile_list) {
     const Scene& s = rs->s;
     int sx0, sy0, sx1, sy1;
     sample_bounds(*film, sx0, sy0, sx1, sy1);
@@ -128,7 +143,9 @@ extern "C" int ref_render_whitted(const ref_scene* rs, const trace_camera* cam, 
     int sbw = sx1 - sx0 + 1;
     int fw = film->crop_x1 - film->crop_x0 + 1;
     std::vector<int64_t> tiles;
-    if (max_tiles > 0 && max_tiles < total) {
+    if (n_tile_list >= 0) {
+        for (int64_t j = 0; j < n_tile_list; ++j) if (tile_list[j] >= 0 && tile_list[j] < total) tiles.push_back(tile_list[j]);
+    } else if (max_tiles > 0 && max_tiles < total) {
         for (int64_t j = 0; j < max_tiles; ++j) tiles.push_back(j * total / max_tiles);
     } else {
         for (int64_t k = 0; k < total; ++k) tiles.push_back(k);

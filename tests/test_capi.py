@@ -33,7 +33,7 @@ def test_struct_layouts(T):
     assert C.sizeof(tl.FilmDesc) == 16 + 8 + 1024 + 4
     assert C.sizeof(tl.Camera) == 64 + 64 + 16
     assert C.sizeof(tl.SceneDesc) == 14 * 8
-    assert C.sizeof(tl.Stats) == 10 * 8
+    assert C.sizeof(tl.Stats) == 12 * 8
 
 
 def test_create_fails_loudly_without_gpu(T):

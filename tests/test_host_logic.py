@@ -1,0 +1,149 @@
+"""Host-side logic that needs no GPU: scene flattening (incl. the nested-BVH splice), the PLY reader, the scene builders
+of the BASELINE.json configs, transformation quirks, multi-GPU partition helpers (gloo, world_size 2)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_transformation_quirk_q1(T):
+    """t1 * t2 multiplies the inverse matrices in the same order (transformations.jl:20-22)."""
+    a, b = T.translate([1, 2, 3]), T.scale(2, 2, 2)
+    ab = a * b
+    assert np.allclose(ab.m, a.m @ b.m) and np.allclose(ab.inv_m, a.inv_m @ b.inv_m)
+    assert not np.allclose(ab.inv_m, np.linalg.inv(ab.m))          # hence not a true inverse
+    assert ab.inv().inv() == ab
+
+
+def test_perspective_is_untransposed(T):
+    p = T.perspective(90.0, 0.01, 1000.0)
+    # scale(inv_tan) * Transformation(Mat4f(...)) with the column-major fill: element [3,2] holds -f*n/(f-n), [2,3] holds 1
+    assert abs(p.m[2, 3] - 1.0) < 1e-6 and abs(p.m[3, 2] + 1000 * 0.01 / (1000 - 0.01)) < 1e-6 and p.m[3, 3] == 0
+
+
+def test_raster_to_camera_matches_survey_emulation(T):
+    """for 1024^2, window (-1,1): pixel (1024,1024) -> (0.01998, 0.02002, -0.99999)."""
+    scene, camera, _ = T.scenes.shadows(resolution=1024)
+    pc = camera.raster_to_camera.point([1024, 1024, 0])
+    assert np.allclose(pc, [0.01998, 0.02002, -0.99999], atol=2e-5)
+    p0 = camera.raster_to_camera.point([0, 0, 0])
+    assert abs(p0[0]) < 1e-4 and abs(p0[2] + 0.99999) < 1e-4
+
+
+def test_flatten_orders_and_materials(T):
+    scene, camera, _ = T.scenes.shadows(resolution=32)
+    flat = scene.flatten()
+    assert len(flat.prims) == 8 and len(flat.spheres) == 4 and len(flat.tri_vertices) == 4
+    assert sorted(flat.prims["original"].tolist()) == list(range(8))
+    assert flat.n_materials == 5 and not flat.has_unshaded
+    # leaves cover the ordered primitive list exactly once
+    meta = flat.nodes["meta"].astype(np.int64)
+    leaves = flat.nodes[(meta >> 30) == 3]
+    assert int(((leaves["meta"].astype(np.int64)) & 0x3FFFFFFF).sum()) == 8
+
+
+def test_nested_bvh_splice_equals_reference_recursion(T):
+    """Splicing a nested BVHAccel's nodes in place of its leaf must give the same hits as tracing each BVH separately
+    and keeping the nearer hit (what the reference's recursive intersect! does)."""
+    rng = np.random.default_rng(0)
+    mk = lambda c: T.GeometricPrimitive(T.Sphere(T.ShapeCore(T.translate(c), False), 0.6, 360.0))
+    inner = [mk(rng.uniform(-4, 0, 3)) for _ in range(6)]
+    outer = [mk(rng.uniform(0, 4, 3)) for _ in range(5)]
+    nested = T.Scene([], T.BVHAccel(outer + [T.BVHAccel(inner)]))
+    flat_all = T.Scene([], T.BVHAccel(outer + inner))
+    o = rng.uniform(-8, 8, (4000, 3)).astype(np.float32)
+    d = (rng.uniform(-4, 4, (4000, 3)) - o).astype(np.float32)
+    p1, t1, _ = oracle_lib.OracleScene(nested.flatten()).intersect(o, d)
+    p2, t2, _ = oracle_lib.OracleScene(flat_all.flatten()).intersect(o, d)
+    assert np.array_equal(p1 != 0, p2 != 0) and np.array_equal(t1, t2)
+    assert (p1 != 0).sum() > 100
+
+
+def test_ply_reader(T):
+    if not os.path.exists(T.scenes.ASSET_PLY):
+        pytest.skip("asset missing")
+    meshes, tris = T.load_triangle_mesh(T.scenes.ASSET_PLY)
+    m = meshes[0]
+    assert m.n_vertices == 44034 and m.n_triangles == 88064 and len(tris) == 88064
+    assert m.indices.min() == 1 and m.indices.max() == 44034          # 1-based like model_loader.jl:35
+    assert m.normals is not None and np.allclose(np.linalg.norm(m.normals, axis=1), 1, atol=1e-3)
+    assert np.array_equal(tris[5].vertices(), m.vertices[m.indices[15:18].astype(np.int64) - 1])
+
+
+def test_tessellated_triangle_counts(T):
+    v, n, idx = T.scenes._uv_sphere((0, 0, 0), 1.0, 266, 264)
+    assert len(idx) == 139920
+    v, n, idx = T.scenes._heightfield(600)
+    assert len(idx) == 720000
+    scene, camera, kw = T.scenes.tessellated(cells=20, stacks=10, slices=8, res=(64, 36))
+    assert scene.aggregate.n_primitives == 2 * 20 * 20 + 2 * (2 * 8 * 9)
+    assert camera.film.pixels.shape == (36, 64, 4)
+
+
+def test_sppm_default_photon_count(T):
+    scene, camera, kw = T.scenes.caustic_glass(resolution=256) if os.path.exists(T.scenes.ASSET_PLY) else T.scenes.shadows(256)
+    integ = T.SPPMIntegrator(camera, 0.075, 5, 100, -1)
+    assert integ.photons_per_iteration == 255 * 255                  # area(crop_bounds), Q22
+
+
+def test_partition_helpers(T):
+    from trace_jl_b200 import distributed as D
+    for world in (1, 2, 3, 8):
+        tiles = [D.tile_shard(527, r, world) for r in range(world)]
+        assert sorted(sum(tiles, [])) == list(range(527))
+        rng = [D.photon_range(1_046_529, r, world) for r in range(world)]
+        assert rng[0][0] == 0 and rng[-1][1] == 1_046_529 and all(rng[i][1] == rng[i + 1][0] for i in range(world - 1))
+    scene, camera, _ = T.scenes.shadows(resolution=1024)
+    assert D.n_sample_tiles(camera.film) == 65 * 65
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["REPO"]); sys.path.insert(0, os.path.join(os.environ["REPO"], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import trace_jl_b200 as T, oracle_lib
+from trace_jl_b200 import distributed as D
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# Whitted: each rank renders its round-robin share of the 16x16 tiles with the CPU oracle into a private film; the
+# all-reduced film must equal the full render (this is the host-side plan whitted.cu / bench.py follow on GPUs).
+scene, camera, _ = T.scenes.shadows(resolution=48)
+osc = oracle_lib.OracleScene(scene.flatten())
+cam, fd = camera.pod(), camera.film.desc()
+n_tiles = D.n_sample_tiles(camera.film)
+mine = D.tile_shard(n_tiles, rank, world)
+film = np.zeros_like(camera.film.pixels)
+import ctypes as C
+L = oracle_lib.lib()
+L.ref_render_whitted_tiles.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64]
+tl = np.array(mine, np.int64)
+assert L.ref_render_whitted_tiles(osc.h, C.byref(cam), C.byref(fd), 2, 4, C.c_uint64(9), oracle_lib.p(film), oracle_lib.p(tl), len(tl)) == 0
+t = torch.from_numpy(film)
+D.allreduce_sum(t)
+full = np.zeros_like(film)
+osc.render_whitted(cam, fd, 2, 4, 9, full, threads=1)
+assert np.allclose(t.numpy(), full, rtol=1e-5, atol=1e-7), np.abs(t.numpy() - full).max()
+# SPPM photon slices partition the iteration
+b, e = D.photon_range(1000, rank, world)
+cnt = torch.tensor([float(e - b)])
+D.allreduce_sum(cnt)
+assert cnt.item() == 1000
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world2_tile_shard_and_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, REPO=ROOT, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2

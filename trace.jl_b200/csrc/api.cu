@@ -71,6 +71,7 @@ extern "C" void trace_destroy(trace_ctx* c) {
     for (auto& b : c->b_query) b.release();
     for (auto& b : c->b_queue) b.release();
     for (auto& b : c->b_misc) b.release();
+    for (auto& e : c->kev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -320,7 +321,7 @@ static int finish_query(trace_ctx* c, int stat_slot, int64_t n, bool is_shadow) 
     if (c->time_kernels) {
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, c->evk0, c->evk1);
-        if (is_shadow) c->stats.ms_shadow += ms; else c->stats.ms_extend += ms;
+        if (is_shadow) { c->stats.ms_shadow += ms; c->stats.shadow_launches++; } else { c->stats.ms_extend += ms; c->stats.extend_launches++; }
     }
     if (c->h_flags[1]) {
         cudaMemsetAsync(ctx_icounters(c) + IC_ERROR, 0, sizeof(int), c->stream);

@@ -56,6 +56,31 @@ struct trace_ctx {
 
     trace_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    // per-launch CUDA-event timing of the traversal kernels (option "time_kernels"), resolved after a stream sync
+    struct KernelEvent { cudaEvent_t a, b; int kind; };
+    std::vector<KernelEvent> kev;
+    size_t kev_used = 0;
+    void kev_begin(int kind) {
+        if (!time_kernels) return;
+        if (kev_used == kev.size()) { KernelEvent e; cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.kind = kind; kev.push_back(e); }
+        kev[kev_used].kind = kind;
+        cudaEventRecord(kev[kev_used].a, stream);
+    }
+    void kev_end() {
+        if (!time_kernels) return;
+        cudaEventRecord(kev[kev_used].b, stream);
+        kev_used++;
+    }
+    void kev_collect() {      // call after the stream has been synchronised
+        for (size_t i = 0; i < kev_used; ++i) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, kev[i].a, kev[i].b) == cudaSuccess) {
+                if (kev[i].kind == 0) { stats.ms_extend += ms; stats.extend_launches++; }
+                else { stats.ms_shadow += ms; stats.shadow_launches++; }
+            }
+        }
+        kev_used = 0;
+    }
 
     SppmState* sppm = nullptr;
 

@@ -533,6 +533,7 @@ static int check_flags(trace_ctx* c, const char* what) {
     int* ic = ctx_icounters(c);
     TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ic + IC_OVERFLOW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->kev_collect();
     if (c->h_flags[1]) { cudaMemsetAsync(ic + IC_ERROR, 0, sizeof(int), c->stream); return c->fail("%s: traversal stack overflow (> 64 pending nodes)", what); }
     if (c->h_flags[0]) { cudaMemsetAsync(ic + IC_OVERFLOW, 0, sizeof(int), c->stream); return c->fail("%s: SPPM grid item capacity exceeded", what); }
     return 0;

@@ -203,6 +203,7 @@ static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long 
     TR_CUDA(c, cudaGetLastError());
     TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ic + IC_OVERFLOW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->kev_collect();
     if (c->h_flags[1]) {
         cudaMemsetAsync(ic + IC_ERROR, 0, sizeof(int), c->stream);
         return c->fail("traversal stack overflow (more than 64 pending nodes; the reference would throw a BoundsError, bvh.jl:222)");

@@ -1,0 +1,107 @@
+"""Multi-GPU drivers: one process per GPU, scene replicated, torch.distributed (NCCL over NVLink) for the two
+exchange steps the path has:
+
+  * Whitted: 16x16 sample tiles are dealt round-robin to the ranks (tile k -> rank k % world, the reference's
+    Threads.@threads loop over tiles, src/integrators/sampler.jl:24); every rank splats into a private full-resolution
+    film; ONE reduce(sum) of the (X, Y, Z, w) film at the end.
+  * SPPM: every rank runs the identical camera pass (same counter-based RNG -> identical visible points and grid),
+    traces its slice of the iteration's photons (Halton index range, src/integrators/sppm.jl:328-336) into a private
+    (Phi, M) buffer, ONE all_reduce(sum) of that buffer per iteration, then the identical per-pixel update.
+
+The host-side partition helpers are pure Python so they can be tested with gloo on CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def tile_shard(n_tiles, rank, world):
+    """Tiles owned by `rank`: k = rank, rank + world, ... (must match whitted.cu)."""
+    return list(range(rank, n_tiles, world))
+
+
+def photon_range(photons_per_iteration, rank, world):
+    """Contiguous photon-index slice [begin, end) of one iteration for `rank`."""
+    p = int(photons_per_iteration)
+    return (p * rank) // world, (p * (rank + 1)) // world
+
+
+def n_sample_tiles(film):
+    sb = film.get_sample_bounds()
+    ext = sb.p_max - sb.p_min
+    return int(np.floor((ext[0] + 16) / 16)) * int(np.floor((ext[1] + 16) / 16))
+
+
+class _DevicePtr:
+    """Zero-copy view of a device buffer for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def allreduce_sum(tensor, group=None):
+    """all_reduce(sum) when a process group exists; identity otherwise.  Backend-agnostic (nccl on GPUs, gloo in tests)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+    return tensor
+
+
+def render_whitted_sharded(ctx, scene, camera, spp, max_depth, seed, film_tensor, rank=0, world=1, group=None, reduce=True):
+    """Render this rank's tiles into `film_tensor` (torch float32 [H, W, 4] on the context's GPU), then reduce to rank 0."""
+    import torch.distributed as dist
+    flat = ctx.upload(scene)
+    if flat.has_unshaded:
+        raise ValueError("every primitive needs a material")
+    ctx.set_option("world", world)
+    ctx.set_option("rank", rank)
+    cam, fd = camera.pod(), camera.film.desc()
+    ctx.check(ctx.lib.trace_render_whitted_device(ctx.h, C.byref(cam), C.byref(fd), int(spp), int(max_depth),
+                                                  C.c_uint64(seed), C.c_void_p(film_tensor.data_ptr())))
+    if reduce and world > 1:
+        dist.reduce(film_tensor, dst=0, op=dist.ReduceOp.SUM, group=group)
+    return film_tensor
+
+
+class SPPMSession:
+    """Stepwise SPPM (trace_sppm_begin / camera_pass / photon_pass / update / image) with photon sharding."""
+
+    def __init__(self, ctx, scene, camera, initial_search_radius, max_depth, photons_per_iteration=-1, seed=0x5EED0001,
+                 rank=0, world=1, group=None):
+        import torch
+        self.ctx, self.camera, self.rank, self.world, self.group = ctx, camera, rank, world, group
+        flat = ctx.upload(scene)
+        if flat.has_unshaded:
+            raise ValueError("every primitive needs a material")
+        if photons_per_iteration <= 0:
+            photons_per_iteration = int(camera.film.crop_bounds.area())
+        self.photons = int(photons_per_iteration)
+        cam, fd = camera.pod(), camera.film.desc()
+        ctx.check(ctx.lib.trace_sppm_begin(ctx.h, C.byref(cam), C.byref(fd), float(initial_search_radius), int(max_depth),
+                                           self.photons, C.c_uint64(seed)))
+        n = C.c_int64()
+        ptr = ctx.lib.trace_sppm_flux_device(ctx.h, C.byref(n))
+        self.flux = torch.as_tensor(_DevicePtr(ptr, n.value), device=f"cuda:{torch.cuda.current_device()}") if world > 1 else None
+        self.iteration = 0
+
+    def step(self):
+        """One SPPM iteration (sppm.jl:153-165) over all ranks."""
+        self.iteration += 1
+        ctx = self.ctx
+        ctx.check(ctx.lib.trace_sppm_camera_pass(ctx.h, self.iteration))
+        b, e = photon_range(self.photons, self.rank, self.world)
+        ctx.check(ctx.lib.trace_sppm_photon_pass(ctx.h, self.iteration, b, e))
+        if self.world > 1:
+            allreduce_sum(self.flux, self.group)
+        ctx.check(ctx.lib.trace_sppm_update(ctx.h))
+
+    def image(self):
+        h, w = self.camera.film.pixels.shape[:2]
+        rgb = np.zeros((h, w, 3), dtype=np.float32)
+        self.ctx.check(self.ctx.lib.trace_sppm_image(self.ctx.h, max(1, self.iteration), _lib.ptr(rgb)))
+        return rgb
+
+    def close(self):
+        self.ctx.check(self.ctx.lib.trace_sppm_end(self.ctx.h))
