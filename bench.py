@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="tess-1M", choices=sorted(WORKLOADS))
-    ap.add_argument("--slab", type=int, default=0)
+    ap.add_argument("--slab", type=int, default=2)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--ref-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -321,7 +321,7 @@ def main():
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"whitted-{args.workload}", "spp": spp, "max_depth": depth,
                           "resolution": list(WORKLOADS[args.workload][0]["res"]), "triangles": int(scene.aggregate.n_primitives),
-                          "bvh_nodes": int(len(flat.nodes)), "slab_test": "literal" if args.slab == 0 else "standard",
+                          "bvh_nodes": int(len(flat.nodes)), "slab_test": {0: "literal (bounds.jl:180-200)", 1: "textbook (not hit-equivalent)", 2: "guarded (literal AND conservative interval; hit-identical, tests/test_gpu_parity.py)"}[args.slab],
                           "parallelism": f"tiles-rr{world}", "l2_policy": "inputs larger than L2 (ray queues + BVH > 126 MB per step)",
                           "rays_per_step": total_rays / args.steps},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,

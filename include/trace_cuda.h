@@ -147,7 +147,8 @@ int         trace_abi_version(void);
 int         trace_create(trace_ctx** out, int device, void* cuda_stream /* NULL: library-owned stream */);
 void        trace_destroy(trace_ctx* ctx);
 const char* trace_last_error(const trace_ctx* ctx);
-/* options: "slab" 0 = literal reference slab test (bounds.jl:180-200), 1 = standard slab (default 0);
+/* options: "slab" 0 = literal reference slab test (bounds.jl:180-200), 1 = textbook slab (measured only: not
+ *          hit-equivalent), 2 = guarded: literal AND a conservative interval test, hit-identical to 0 (default 2);
  *          "batch" camera samples per wavefront batch; "count_nodes" 0/1; "time_kernels" 0/1;
  *          "rank"/"world" shard selection for renders (tiles / photons). */
 int         trace_set_option(trace_ctx* ctx, const char* key, int64_t value);

@@ -85,7 +85,7 @@ extern "C" const char* trace_last_error(const trace_ctx* c) { return c ? c->err.
 
 extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     if (!c || !key) return 1;
-    if (!strcmp(key, "slab")) { if (v != 0 && v != 1) return c->fail("slab must be 0 or 1"); c->slab = (int)v; }
+    if (!strcmp(key, "slab")) { if (v < 0 || v > 2) return c->fail("slab must be 0 (literal), 1 (textbook) or 2 (guarded)"); c->slab = (int)v; }
     else if (!strcmp(key, "batch")) { if (v < 1024) return c->fail("batch too small"); c->batch = v; }
     else if (!strcmp(key, "count_nodes")) c->count_nodes = v != 0;
     else if (!strcmp(key, "time_kernels")) c->time_kernels = v != 0;
@@ -156,6 +156,22 @@ extern "C" int trace_scene_upload(trace_ctx* c, const trace_scene_desc* d) {
         b.x = n.bmax[1]; b.y = n.bmax[2];
         memcpy(&b.z, &n.offset, 4); memcpy(&b.w, &n.meta, 4);
         nodes[2 * i] = a; nodes[2 * i + 1] = b;
+    }
+    // device-only meta bit 29: "an analytic sphere lives in this subtree" (see traverse.cuh). Preorder => children have
+    // larger indices than their parent, so one reverse sweep propagates it.
+    {
+        std::vector<uint8_t> below((size_t)d->n_nodes, 0);
+        for (int64_t i = d->n_nodes - 1; i >= 0; --i) {
+            const trace_bvh_node& n = d->nodes[i];
+            uint8_t f = 0;
+            if ((n.meta >> 30) == 3) {
+                const uint32_t cnt = n.meta & 0x3FFFFFFFu;
+                if (cnt >= 0x20000000u) return c->fail("scene: leaf %lld holds too many primitives", (long long)i);
+                for (uint32_t k = 0; k < cnt; ++k) if (d->prims[n.offset + k].kind == TRACE_PRIM_SPHERE) f = 1;
+            } else f = below[i + 1] | below[n.offset];
+            below[i] = f;
+            if (f) { uint32_t m; memcpy(&m, &nodes[2 * i + 1].w, 4); m |= 0x20000000u; memcpy(&nodes[2 * i + 1].w, &m, 4); }
+        }
     }
     std::vector<float4> prims((size_t)d->n_prims * 3), tnorm((size_t)d->n_prims * 3);
     for (int64_t i = 0; i < d->n_prims; ++i) {
@@ -243,6 +259,14 @@ extern "C" int trace_scene_upload(trace_ctx* c, const trace_scene_desc* d) {
     s.lights = c->b_lights.as<DeviceLight>();
     s.n_nodes = (int)d->n_nodes; s.n_prims = (int)d->n_prims; s.n_spheres = (int)d->n_spheres;
     s.n_materials = (int)d->n_materials; s.n_lights = (int)d->n_lights;
+    s.scene_scale = 0.0f;
+    if (d->n_nodes > 0) {
+        for (int k = 0; k < 3; ++k) {
+            const float a = fabsf(d->nodes[0].bmin[k]), b = fabsf(d->nodes[0].bmax[k]);
+            if (std::isfinite(a)) s.scene_scale = fmaxf(s.scene_scale, a);
+            if (std::isfinite(b)) s.scene_scale = fmaxf(s.scene_scale, b);
+        }
+    }
     c->have_scene = true;
     sppm_free(c);
     return 0;
@@ -285,6 +309,9 @@ static int launch_intersect(trace_ctx* c, const float4* ro, const float4* rd, in
     if (c->slab == 0) {
         if (c->count_nodes) k_intersect<0, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
         else k_intersect<0, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
+    } else if (c->slab == 2) {
+        if (c->count_nodes) k_intersect<2, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
+        else k_intersect<2, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
     } else {
         if (c->count_nodes) k_intersect<1, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
         else k_intersect<1, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
@@ -302,6 +329,9 @@ static int launch_occluded(trace_ctx* c, const float4* ro, const float4* rd, int
     if (c->slab == 0) {
         if (c->count_nodes) k_occluded<0, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
         else k_occluded<0, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
+    } else if (c->slab == 2) {
+        if (c->count_nodes) k_occluded<2, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
+        else k_occluded<2, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
     } else {
         if (c->count_nodes) k_occluded<1, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
         else k_occluded<1, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);

@@ -36,7 +36,7 @@ struct trace_ctx {
     std::string err;
 
     // options
-    int slab = 0;                 // 0 literal reference slab test, 1 standard slab test
+    int slab = 2;                 // 0 literal reference slab test, 1 textbook (not hit-equivalent), 2 guarded (default)
     int64_t batch = 1 << 21;      // camera samples per wavefront batch
     int count_nodes = 0;
     int time_kernels = 0;

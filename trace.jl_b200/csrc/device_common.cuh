@@ -91,6 +91,7 @@ struct DeviceScene {
     const DeviceMaterial* materials;
     const DeviceLight* lights;
     int n_nodes, n_prims, n_spheres, n_materials, n_lights;
+    float scene_scale;        // largest |coordinate| of the root bounds (slack of the guarded slab test)
 };
 struct DeviceCamera {
     float r2c[16], c2w[16];

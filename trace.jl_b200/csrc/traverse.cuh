@@ -17,9 +17,17 @@ struct RayPrep {            // quantities that depend on the ray only
     int kz;                 // permutation of the triangle test
     float ox, oy, oz;       // o permuted
     float Sx, Sy, Sz;       // shear
+    float mx, my, mz;       // SLAB 2: per-axis slack of the conservative interval, in units of t
 };
 
-__device__ __forceinline__ RayPrep prepare_ray(float3 o, float3 d) {
+// Spatial slack of the conservative box test (SLAB 2), relative to the largest coordinate in play: 2^-17 ~ 7.6e-6,
+// i.e. ~64 float ULPs - far above the rounding of the slab products and of the watertight triangle test, far below
+// any triangle size.
+#define TR_GUARD_REL 7.62939453125e-6f
+#define TR_NODE_SPHERE_BELOW 0x20000000u   // device-side node meta bit 29, set at upload
+#define TR_NODE_COUNT_MASK 0x1FFFFFFFu
+
+__device__ __forceinline__ RayPrep prepare_ray(float3 o, float3 d, float scene_scale = 0.0f) {
     RayPrep r;
     // check_direction!: -0.0 -> +0.0 (x ≈ 0f0 is x == 0)
     if (d.x == 0.0f) d.x = 0.0f;
@@ -40,25 +48,47 @@ __device__ __forceinline__ RayPrep prepare_ray(float3 o, float3 d) {
     else              { dx = d.x; dy = d.y; dz = d.z; r.ox = o.x; r.oy = o.y; r.oz = o.z; }
     float denom = 1.0f / dz;
     r.Sx = -dx * denom; r.Sy = -dy * denom; r.Sz = denom;
+    const float slack = TR_GUARD_REL * fmaxf(scene_scale, fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z))));
+    r.mx = slack * fabsf(r.inv.x); r.my = slack * fabsf(r.inv.y); r.mz = slack * fabsf(r.inv.z);
     return r;
 }
 
+// SLAB 0: the reference's test, literally (bounds.jl:180-200; line 191 keeps the LARGER y far bound, Q26).
+// SLAB 1: the textbook test. NOT hit-equivalent to the reference (it drops rays grazing zero-thickness boxes): kept
+//         only as a measured comparison, never a default.
+// SLAB 2: "guarded": a node is entered iff the reference's test accepts it AND a conservative interval test (every
+//         slab interval widened by the slack r.m*, NaN-transparent) cannot prove that the ray segment (0, t_max] misses
+//         the box.  The visited set is a subset of the reference's, in the same order; a node is skipped only when
+//         the ray provably stays clear of everything inside it, so hits, ties and t are the reference's.
+// The guard is switched off (literal test only) for nodes whose subtree holds an analytic sphere
+// (TR_NODE_SPHERE_BELOW): the reference's float32 quadratic (sphere.jl:39-54) is ill-conditioned for a small sphere
+// seen from far away - b*b - 4ac cancels catastrophically and rays passing up to ~|o|^2 eps / 2r OUTSIDE the sphere
+// still "hit" it at t ~ -b/2a.  The reference reports those hits (its loose box test lets the ray into the node), so
+// the guarded variant must too; no fixed slack bounds that error.  Triangles have no such problem: the watertight
+// test's error is a few ULPs of the coordinates.
 template <int SLAB>
 __device__ __forceinline__ bool slab_test(const float4 n0, const float4 n1, const RayPrep& r, float tmax) {
     // bmin = (n0.x, n0.y, n0.z), bmax = (n0.w, n1.x, n1.y)
-    float tx_min = ((r.nx ? n0.w : n0.x) - r.o.x) * r.inv.x;
-    float tx_max = ((r.nx ? n0.x : n0.w) - r.o.x) * r.inv.x;
-    float ty_min = ((r.ny ? n1.x : n0.y) - r.o.y) * r.inv.y;
-    float ty_max = ((r.ny ? n0.y : n1.x) - r.o.y) * r.inv.y;
-    if (tx_min > ty_max || ty_min > tx_max) return false;
-    if (ty_min > tx_min) tx_min = ty_min;
-    if (SLAB == 0) { if (ty_max > tx_max) tx_max = ty_max; }     // bounds.jl:191 keeps the larger (Q26)
-    else           { if (ty_max < tx_max) tx_max = ty_max; }
-    float tz_min = ((r.nz ? n1.y : n0.z) - r.o.z) * r.inv.z;
-    float tz_max = ((r.nz ? n0.z : n1.y) - r.o.z) * r.inv.z;
-    if (tx_min > tz_max || tz_min > tx_max) return false;
-    if (tz_min > tx_min) tx_min = tz_min;
-    if (tz_max < tx_max) tx_max = tz_max;
+    const float ax0 = ((r.nx ? n0.w : n0.x) - r.o.x) * r.inv.x;
+    const float ax1 = ((r.nx ? n0.x : n0.w) - r.o.x) * r.inv.x;
+    const float ay0 = ((r.ny ? n1.x : n0.y) - r.o.y) * r.inv.y;
+    const float ay1 = ((r.ny ? n0.y : n1.x) - r.o.y) * r.inv.y;
+    const float az0 = ((r.nz ? n1.y : n0.z) - r.o.z) * r.inv.z;
+    const float az1 = ((r.nz ? n0.z : n1.y) - r.o.z) * r.inv.z;
+    if (SLAB == 2 && !(__float_as_uint(n1.w) & TR_NODE_SPHERE_BELOW)) {
+        // fmaxf / fminf drop NaNs (0 * Inf on an axis the ray is parallel to), so such an axis never rejects
+        const float t_enter = fmaxf(fmaxf(ax0 - r.mx, ay0 - r.my), az0 - r.mz);
+        const float t_exit = fminf(fminf(ax1 + r.mx, ay1 + r.my), az1 + r.mz);
+        if (t_enter > t_exit || t_exit < 0.0f || t_enter > tmax + fabsf(tmax) * TR_GUARD_REL) return false;
+    }
+    float tx_min = ax0, tx_max = ax1;
+    if (tx_min > ay1 || ay0 > tx_max) return false;
+    if (ay0 > tx_min) tx_min = ay0;
+    if (SLAB == 1) { if (ay1 < tx_max) tx_max = ay1; }
+    else           { if (ay1 > tx_max) tx_max = ay1; }
+    if (tx_min > az1 || az0 > tx_max) return false;
+    if (az0 > tx_min) tx_min = az0;
+    if (az1 < tx_max) tx_max = az1;
     return tx_min < tmax && tx_max > 0.0f;
 }
 
@@ -162,7 +192,7 @@ __device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3
                                          unsigned long long* counters, int* error_flag) {
     out.prim = 0; out.t = tmax; out.b0 = 0.0f; out.b1 = 0.0f;
     if (sc.n_nodes == 0) return false;
-    const RayPrep r = prepare_ray(o, d);
+    const RayPrep r = prepare_ray(o, d, sc.scene_scale);
     uint32_t stack[TR_STACK_SIZE];
     int sp = 0;
     uint32_t cur = 0;
@@ -175,7 +205,7 @@ __device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3
         bool descend = false;
         if (slab_test<SLAB>(n0, n1, r, tmax)) {
             const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
-            const uint32_t count = meta & 0x3FFFFFFFu;
+            const uint32_t count = meta & TR_NODE_COUNT_MASK;
             if ((meta >> 30) == 3u) {     // leaf (a zero-primitive leaf has invalid bounds and never gets here, Q16/Q17)
                 for (uint32_t i = 0; i < count; ++i) {
                     const uint32_t pi = offset + i;

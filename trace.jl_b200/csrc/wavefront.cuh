@@ -50,6 +50,7 @@ template <class... Args>
 static void launch_extend(trace_ctx* c, int grid, Args... args) {
     c->kev_begin(0);
     if (c->slab == 0) { if (c->count_nodes) k_wh_extend<0, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_extend<0, false><<<grid, 128, 0, c->stream>>>(args...); }
+    else if (c->slab == 2) { if (c->count_nodes) k_wh_extend<2, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_extend<2, false><<<grid, 128, 0, c->stream>>>(args...); }
     else              { if (c->count_nodes) k_wh_extend<1, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_extend<1, false><<<grid, 128, 0, c->stream>>>(args...); }
     c->stats.kernel_launches++;
     c->kev_end();
@@ -58,6 +59,7 @@ template <class... Args>
 static void launch_shadow(trace_ctx* c, int grid, Args... args) {
     c->kev_begin(1);
     if (c->slab == 0) { if (c->count_nodes) k_wh_shadow<0, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_shadow<0, false><<<grid, 128, 0, c->stream>>>(args...); }
+    else if (c->slab == 2) { if (c->count_nodes) k_wh_shadow<2, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_shadow<2, false><<<grid, 128, 0, c->stream>>>(args...); }
     else              { if (c->count_nodes) k_wh_shadow<1, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_shadow<1, false><<<grid, 128, 0, c->stream>>>(args...); }
     c->stats.kernel_launches++;
     c->kev_end();
