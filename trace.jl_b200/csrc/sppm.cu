@@ -312,7 +312,6 @@ __global__ void __launch_bounds__(256) k_photon_generate(SppmLaunch L) {
 __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
     const int cur = (level - 1) & 1, nxt = level & 1;
     const int n = min(L.counters[level], L.cap);
-    unsigned int deposits = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 h = L.hits[i];
         const uint32_t prim1 = __float_as_uint(h.y);
@@ -328,26 +327,16 @@ __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
         const Interaction it = build_interaction(L.sc, prim, xyz(o4), d, h.z, h.w, b2);
         const float3 wo = -d;
         if (level > 1) {
-            // deposit into every visible point of the hashed cell within its radius (sppm.jl:377-403)
+            // photon landed at depth > 1: queue a deposit request for k_photon_deposit (sppm.jl:377-403)
             const GridParams& g = *L.grid;
             int cell[3];
             if (g.valid && to_grid(g, it.p, cell)) {
                 const unsigned int hsh = grid_hash(cell[0], cell[1], cell[2], (unsigned int)L.npix);
-                const unsigned int e0 = L.cell_start[hsh], e1 = L.cell_start[hsh + 1];
-                for (unsigned int e = e0; e < e1; ++e) {
-                    const unsigned int pix = L.cell_items[e];
-                    const float4 A = L.vpA[pix];
-                    const float3 dd = xyz(A) - it.p;
-                    if (dot3(dd, dd) > A.w) continue;
-                    const float4 Bv = L.vpB[pix];
-                    Frame vf;
-                    vf.ns = xyz(L.vpC[pix]); vf.ss = xyz(L.vpD[pix]); vf.ng = xyz(L.vpE[pix]);
-                    vf.ts = cross3(vf.ns, vf.ss);
-                    LobeSet vl;
-                    material_lobes(L.sc.materials[__float_as_uint(Bv.w)], true, vl);
-                    const float3 phi = beta * bsdf_f(vl, vf, xyz(Bv), wo, LB_ALL);
-                    atomicAdd(&L.flux[pix], make_float4(phi.x, phi.y, phi.z, 1.0f));
-                    deposits++;
+                if (L.cell_start[hsh + 1] > L.cell_start[hsh]) {
+                    const int q = queue_claim(&L.counters[32 + level]);
+                    L.so[q] = f4(it.p, __uint_as_float(hsh));
+                    L.sd[q] = f4(wo, 0.0f);
+                    L.sc_contrib[q] = f4(beta, 0.0f);
                 }
             }
         }
@@ -369,7 +358,41 @@ __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
         L.rd[nxt][qi] = f4(bs.wi, d4.w);
         L.rw[nxt][qi] = w4;                                      // beta is NOT updated (Q7)
     }
-    if (deposits) atomicAdd(&L.stats[ST_DEPOSITS], (unsigned long long)deposits);
+}
+
+// One WARP per deposit request: the 32 lanes stride over the hashed cell's CSR list (coalesced index loads), test
+// |vp.p - p|^2 <= r^2 and, for accepted visible points, evaluate vp.bsdf(vp.wo, -d) and add (beta * f, 1) to
+// (Phi, M) with one 128-bit vector atomic.  Lists are long where visible points are dense (cell edge ~ max radius,
+// pixel footprint << radius: thousands of entries per cell), so a thread-per-photon loop serialises on its longest
+// list; a warp per request keeps every lane busy and the loads coalesced.
+__global__ void __launch_bounds__(128) k_photon_deposit(SppmLaunch L, int level) {
+    const int n = min(L.counters[32 + level], L.cap);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned int deposits = 0;
+    for (int r = warp; r < n; r += n_warps) {
+        const float4 P = L.so[r], WO = L.sd[r], B = L.sc_contrib[r];
+        const float3 p = xyz(P), wo = xyz(WO), beta = xyz(B);
+        const unsigned int hsh = __float_as_uint(P.w);
+        const unsigned int e0 = L.cell_start[hsh], e1 = L.cell_start[hsh + 1];
+        for (unsigned int e = e0 + lane; e < e1; e += 32) {
+            const unsigned int pix = L.cell_items[e];
+            const float4 A = L.vpA[pix];
+            const float3 dd = xyz(A) - p;
+            if (dot3(dd, dd) > A.w) continue;
+            const float4 Bv = L.vpB[pix];
+            Frame vf;
+            vf.ns = xyz(L.vpC[pix]); vf.ss = xyz(L.vpD[pix]); vf.ng = xyz(L.vpE[pix]);
+            vf.ts = cross3(vf.ns, vf.ss);
+            LobeSet vl;
+            material_lobes(L.sc.materials[__float_as_uint(Bv.w)], true, vl);
+            const float3 phi = beta * bsdf_f(vl, vf, xyz(Bv), wo, LB_ALL);
+            atomicAdd(&L.flux[pix], make_float4(phi.x, phi.y, phi.z, 1.0f));
+            deposits++;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) deposits += __shfl_xor_sync(0xffffffffu, deposits, off);
+    if (lane == 0 && deposits) atomicAdd(&L.stats[ST_DEPOSITS], (unsigned long long)deposits);
 }
 
 // ---------------------------------------------------------------- per-iteration update and image (sppm.jl:438-472)
@@ -418,11 +441,12 @@ __global__ void k_sppm_init(SppmLaunch L, float r0) {
     }
 }
 
-__global__ void k_sppm_stats(int* counters, unsigned long long* stats, int max_depth, int cap) {
+__global__ void k_sppm_stats(int* counters, unsigned long long* stats, int max_depth, int cap, int count_shadow) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long e = 0, s = 0;
         for (int l = 1; l <= max_depth; ++l) { e += min(counters[l], cap); s += counters[32 + l]; }
-        stats[ST_RAYS_EXTEND] += e; stats[ST_RAYS_SHADOW] += s;
+        stats[ST_RAYS_EXTEND] += e;
+        if (count_shadow) stats[ST_RAYS_SHADOW] += s;      // in the photon pass slots 32.. count deposit requests
     }
 }
 
@@ -561,7 +585,7 @@ extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
         launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
                       (const int*)(ic + 32 + level), L.cap, L.Ld, st + ST_NODES, ic + IC_ERROR);
     }
-    k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap);
+    k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap, 1);
     // hash grid of the visible points: bounds -> resolution -> count -> scan -> fill
     const int n_cells = L.npix + 1;
     const int scan_blocks = (n_cells + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
@@ -603,8 +627,12 @@ extern "C" int trace_sppm_photon_pass(trace_ctx* c, int iteration, int64_t begin
                           st + ST_NODES, ic + IC_ERROR);
             k_photon_shade<<<g_trav, 128, 0, c->stream>>>(L, level);
             c->stats.kernel_launches++;
+            if (level > 1) {
+                k_photon_deposit<<<g_trav, 128, 0, c->stream>>>(L, level);
+                c->stats.kernel_launches++;
+            }
         }
-        k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap);
+        k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap, 0);
         c->stats.kernel_launches++;
     }
     TR_CUDA(c, cudaGetLastError());
