@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--workload", default="tess-1M", choices=sorted(WORKLOADS))
     ap.add_argument("--slab", type=int, default=2)
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--persist", type=int, default=0)
     ap.add_argument("--ref-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sppm", action="store_true")
@@ -165,6 +166,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     ctx = T.Context(local, stream=stream)
     ctx.set_option("slab", args.slab)
+    ctx.set_option("persist", args.persist)
     if args.batch:
         ctx.set_option("batch", args.batch)
 

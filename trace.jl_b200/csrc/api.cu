@@ -88,6 +88,7 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     if (!strcmp(key, "slab")) { if (v < 0 || v > 2) return c->fail("slab must be 0 (literal), 1 (textbook) or 2 (guarded)"); c->slab = (int)v; }
     else if (!strcmp(key, "batch")) { if (v < 1024) return c->fail("batch too small"); c->batch = v; }
     else if (!strcmp(key, "count_nodes")) c->count_nodes = v != 0;
+    else if (!strcmp(key, "persist")) c->persist = v != 0;
     else if (!strcmp(key, "time_kernels")) c->time_kernels = v != 0;
     else if (!strcmp(key, "rank")) c->rank = (int)v;
     else if (!strcmp(key, "world")) { if (v < 1) return c->fail("world must be >= 1"); c->world = (int)v; }
@@ -307,14 +308,14 @@ static int launch_intersect(trace_ctx* c, const float4* ro, const float4* rd, in
     const int grid = (int)std::min<int64_t>((n + 127) / 128, (int64_t)persistent_grid(c, 16));
     if (c->time_kernels) cudaEventRecord(c->evk0, c->stream);
     if (c->slab == 0) {
-        if (c->count_nodes) k_intersect<0, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
-        else k_intersect<0, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
+        if (c->count_nodes) k_intersect<0, true><<<std::min(grid, occupancy_grid(c, k_intersect<0, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
+        else k_intersect<0, false><<<std::min(grid, occupancy_grid(c, k_intersect<0, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
     } else if (c->slab == 2) {
-        if (c->count_nodes) k_intersect<2, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
-        else k_intersect<2, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
+        if (c->count_nodes) k_intersect<2, true><<<std::min(grid, occupancy_grid(c, k_intersect<2, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
+        else k_intersect<2, false><<<std::min(grid, occupancy_grid(c, k_intersect<2, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
     } else {
-        if (c->count_nodes) k_intersect<1, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
-        else k_intersect<1, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
+        if (c->count_nodes) k_intersect<1, true><<<std::min(grid, occupancy_grid(c, k_intersect<1, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
+        else k_intersect<1, false><<<std::min(grid, occupancy_grid(c, k_intersect<1, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
     }
     if (c->time_kernels) cudaEventRecord(c->evk1, c->stream);
     TR_CUDA(c, cudaGetLastError());
@@ -327,14 +328,14 @@ static int launch_occluded(trace_ctx* c, const float4* ro, const float4* rd, int
     const int grid = (int)std::min<int64_t>((n + 127) / 128, (int64_t)persistent_grid(c, 16));
     if (c->time_kernels) cudaEventRecord(c->evk0, c->stream);
     if (c->slab == 0) {
-        if (c->count_nodes) k_occluded<0, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
-        else k_occluded<0, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
+        if (c->count_nodes) k_occluded<0, true><<<std::min(grid, occupancy_grid(c, k_occluded<0, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
+        else k_occluded<0, false><<<std::min(grid, occupancy_grid(c, k_occluded<0, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
     } else if (c->slab == 2) {
-        if (c->count_nodes) k_occluded<2, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
-        else k_occluded<2, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
+        if (c->count_nodes) k_occluded<2, true><<<std::min(grid, occupancy_grid(c, k_occluded<2, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
+        else k_occluded<2, false><<<std::min(grid, occupancy_grid(c, k_occluded<2, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
     } else {
-        if (c->count_nodes) k_occluded<1, true><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
-        else k_occluded<1, false><<<grid, 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
+        if (c->count_nodes) k_occluded<1, true><<<std::min(grid, occupancy_grid(c, k_occluded<1, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
+        else k_occluded<1, false><<<std::min(grid, occupancy_grid(c, k_occluded<1, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
     }
     if (c->time_kernels) cudaEventRecord(c->evk1, c->stream);
     TR_CUDA(c, cudaGetLastError());

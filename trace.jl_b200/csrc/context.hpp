@@ -37,8 +37,10 @@ struct trace_ctx {
 
     // options
     int slab = 2;                 // 0 literal reference slab test, 1 textbook (not hit-equivalent), 2 guarded (default)
-    int64_t batch = 1 << 21;      // camera samples per wavefront batch
+    int64_t batch = 1 << 26;      // camera samples per wavefront batch (queues: ~350 B per sample, allocated for min(batch, work))
     int count_nodes = 0;
+    int persist = 0;              // persistent warps with dynamic ray fetch (measured slower on B200: kept as an option)
+    int work_slot = 0;
     int time_kernels = 0;
     int rank = 0, world = 1;
 
@@ -103,7 +105,7 @@ struct trace_ctx {
 
 // u64 device stats block layout (ctx->b_counters, after the int counters)
 enum { ST_RAYS_EXTEND = 0, ST_RAYS_SHADOW = 1, ST_NODES = 2, ST_PRIMS = 3, ST_DEPOSITS = 4, ST_COUNT = 8 };
-static const int TR_INT_COUNTERS = 64;     // ints at the start of b_counters
+static const int TR_INT_COUNTERS = 128;    // ints at the start of b_counters (64..127: work counters of persistent launches)
 // int counter slots
 enum { IC_OVERFLOW = 60, IC_ERROR = 61 };
 
@@ -114,6 +116,27 @@ inline unsigned long long* ctx_stats64(trace_ctx* c) {
 
 // grid for persistent grid-stride kernels: a multiple of the SM count
 inline int persistent_grid(const trace_ctx* c, int blocks_per_sm) { return c->num_sms * blocks_per_sm; }
+
+// Grid = SM count x resident CTAs per SM of THIS kernel (occupancy API), so a grid-stride kernel runs as exactly one
+// full wave: with a fixed 16 CTAs/SM the 69-register traversal kernels (7 resident) ran 2.29 waves, the last one 29 %
+// full (ncu: sm__warps_active 29 % of peak against a 44 % theoretical).
+#ifdef __CUDACC__
+#include <map>
+template <class K>
+inline int occupancy_grid(const trace_ctx* c, K kernel, int block_size) {
+    static std::map<const void*, int> cache;
+    const void* key = (const void*)kernel;
+    auto it = cache.find(key);
+    int per_sm;
+    if (it != cache.end()) per_sm = it->second;
+    else {
+        per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block_size, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        cache[key] = per_sm;
+    }
+    return c->num_sms * per_sm;
+}
+#endif
 
 // implemented in api.cu
 int ctx_device_film(trace_ctx* ctx, const trace_film_desc* film, DeviceFilm* out, DevBuf* table_buf);

@@ -573,6 +573,7 @@ extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
     int* ic = ctx_icounters(c);
     unsigned long long* st = ctx_stats64(c);
     TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->stream));
+    TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), c->stream)); c->work_slot = 0;
     const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
     k_sppm_cam_generate<<<g_stream, 256, 0, c->stream>>>(L);
     c->stats.kernel_launches++;
@@ -580,7 +581,7 @@ extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
         const int cur = (level - 1) & 1;
         launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap, L.hits,
                       st + ST_NODES, ic + IC_ERROR);
-        k_sppm_cam_shade<<<g_trav, 128, 0, c->stream>>>(L, level);
+        k_sppm_cam_shade<<<occupancy_grid(c, k_sppm_cam_shade, 128), 128, 0, c->stream>>>(L, level);
         c->stats.kernel_launches++;
         launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
                       (const int*)(ic + 32 + level), L.cap, L.Ld, st + ST_NODES, ic + IC_ERROR);
@@ -619,16 +620,17 @@ extern "C" int trace_sppm_photon_pass(trace_ctx* c, int iteration, int64_t begin
         L.photon_begin = b;
         L.n_photons = (int)std::min<int64_t>(s->photon_cap, end - b);
         TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->stream));
+    TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), c->stream)); c->work_slot = 0;
         k_photon_generate<<<g_stream, 256, 0, c->stream>>>(L);
         c->stats.kernel_launches++;
         for (int level = 1; level <= L.max_depth; ++level) {
             const int cur = (level - 1) & 1;
             launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap, L.hits,
                           st + ST_NODES, ic + IC_ERROR);
-            k_photon_shade<<<g_trav, 128, 0, c->stream>>>(L, level);
+            k_photon_shade<<<occupancy_grid(c, k_photon_shade, 128), 128, 0, c->stream>>>(L, level);
             c->stats.kernel_launches++;
             if (level > 1) {
-                k_photon_deposit<<<g_trav, 128, 0, c->stream>>>(L, level);
+                k_photon_deposit<<<occupancy_grid(c, k_photon_deposit, 128), 128, 0, c->stream>>>(L, level);
                 c->stats.kernel_launches++;
             }
         }

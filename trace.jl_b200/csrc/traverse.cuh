@@ -187,6 +187,11 @@ struct HitRecord {
 };
 
 // Returns true when something was hit. ANY: stops at the first accepted primitive (intersect_p).
+// The loop is the reference's (bvh.jl:221-257): box-test the current node; leaf -> test its primitives in order, each
+// accepted closest hit shrinks t_max; interior -> near child next (sign of d[split_axis]), far child pushed untested.
+// Measured and rejected on B200 (profiles/r1_experiments.md): box-testing both children at their parent (0.7x), a
+// min/max reformulation of the slab test with fewer instructions (0.75-0.98x), persistent warps with dynamic ray
+// fetch (0.85x, kept below as option "persist").
 template <int SLAB, bool ANY, bool COUNT>
 __device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3 d, float tmax, HitRecord& out,
                                          unsigned long long* counters, int* error_flag) {
@@ -247,4 +252,96 @@ __device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3
 done:
     if (COUNT && counters) { atomicAdd(&counters[0], (unsigned long long)n_nodes); atomicAdd(&counters[1], (unsigned long long)n_prims); }
     return found;
+}
+
+// ------------------------------------------------------------------ persistent warps with dynamic ray fetch
+// The plain kernels give each thread a fixed slice of the queue; a warp then runs until its SLOWEST ray is done
+// (ncu: 20 of 32 lanes active on average for primary rays, 13-17 for secondary / shadow rays).  Here a warp keeps
+// traversing and, whenever at least TR_REFILL_LANES lanes have finished, those lanes claim the next rays of the queue
+// from a device-side counter (one warp-aggregated atomic) - the "persistent threads + dynamic fetch" scheme of
+// Aila & Laine.  Each lane runs exactly the loop of traverse<>() on its ray, one node per iteration, so per-ray
+// results are unchanged.
+#define TR_REFILL_LANES 8
+
+template <int SLAB, bool ANY, class Finish>
+__device__ __forceinline__ void trace_persistent(const DeviceScene& sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
+                                                 int n, int* work_counter, int* error_flag, Finish finish) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool have = false, exhausted = false;
+    int ray = 0;
+    RayPrep r;
+    float tmax = 0.0f;
+    uint32_t cur = 0;
+    int sp = 0;
+    uint32_t stack[TR_STACK_SIZE];
+    HitRecord out;
+    out.prim = 0; out.t = 0.0f; out.b0 = 0.0f; out.b1 = 0.0f;
+    if (sc.n_nodes == 0) n = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, !have);
+        if (idle != 0u && !exhausted && (__popc(idle) >= TR_REFILL_LANES || idle == full)) {
+            int base = 0;
+            const int want = __popc(idle);
+            if (lane == (unsigned)(__ffs(idle) - 1)) base = atomicAdd(work_counter, want);
+            base = __shfl_sync(full, base, __ffs(idle) - 1);
+            if (base + want >= n) exhausted = true;
+            const int mine = base + __popc(idle & lt_mask);
+            if (!have && mine < n) {
+                const float4 o4 = ro[mine], d4 = rd[mine];
+                r = prepare_ray(xyz(o4), xyz(d4), sc.scene_scale);
+                tmax = o4.w; ray = mine; cur = 0; sp = 0; have = true;
+                out.prim = 0; out.t = tmax; out.b0 = 0.0f; out.b1 = 0.0f;
+            }
+        }
+        if (__ballot_sync(full, have) == 0u) { if (exhausted) break; else continue; }
+        if (have) {
+            const float4 n0 = __ldg(&sc.nodes[2 * cur]);
+            const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
+            bool descend = false, done = false;
+            if (slab_test<SLAB>(n0, n1, r, tmax)) {
+                const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
+                if ((meta >> 30) == 3u) {
+                    const uint32_t count = meta & TR_NODE_COUNT_MASK;
+                    for (uint32_t i = 0; i < count; ++i) {
+                        const uint32_t pi = offset + i;
+                        const float4 a = __ldg(&sc.prims[3 * pi]);
+                        const uint32_t tag = __float_as_uint(a.w);
+                        if (tag == 0u) {
+                            const float4 b = __ldg(&sc.prims[3 * pi + 1]);
+                            const float4 c = __ldg(&sc.prims[3 * pi + 2]);
+                            float t, b0, b1, b2;
+                            if (triangle_test(a, b, c, r, tmax, t, b0, b1, b2)) {
+                                out.prim = pi + 1;
+                                if (ANY) { done = true; break; }
+                                tmax = t; out.t = t; out.b0 = b0; out.b1 = b1;
+                            }
+                        } else if (tag & TR_PRIM_SPHERE_BIT) {
+                            SphereHitInfo sh;
+                            if (sphere_test(sc.spheres[tag & 0x3FFFFFFFu], r.o, r.d, tmax, sh)) {
+                                out.prim = pi + 1;
+                                if (ANY) { done = true; break; }
+                                tmax = sh.t; out.t = sh.t; out.b0 = 0.0f; out.b1 = 0.0f;
+                            }
+                        }
+                    }
+                } else {
+                    const uint32_t axis = meta >> 30;
+                    const bool neg = axis == 0 ? r.nx : (axis == 1 ? r.ny : r.nz);
+                    if (sp >= TR_STACK_SIZE) { if (error_flag) *error_flag = 1; done = true; }
+                    else {
+                        if (neg) { stack[sp++] = cur + 1; cur = offset; }
+                        else     { stack[sp++] = offset; cur = cur + 1; }
+                        descend = true;
+                    }
+                }
+            }
+            if (!descend && !done) {
+                if (sp == 0) done = true;
+                else cur = stack[--sp];
+            }
+            if (done) { finish(ray, out); have = false; }
+        }
+    }
 }

@@ -35,6 +35,29 @@ __global__ void __launch_bounds__(128) k_wh_shadow(DeviceScene sc, const float4*
     }
 }
 
+// persistent-warp variants (dynamic ray fetch, traverse.cuh)
+template <int SLAB>
+__global__ void __launch_bounds__(128) k_wh_extend_p(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
+                                                     const int* __restrict__ count, int cap, float4* __restrict__ hits,
+                                                     int* work_counter, int* error_flag) {
+    const int n = min(*count, cap);
+    trace_persistent<SLAB, false>(sc, ro, rd, n, work_counter, error_flag, [&](int ray, const HitRecord& h) {
+        hits[ray] = make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1);
+    });
+}
+template <int SLAB>
+__global__ void __launch_bounds__(128) k_wh_shadow_p(DeviceScene sc, const float4* __restrict__ so, const float4* __restrict__ sd,
+                                                     const float4* __restrict__ contrib, const int* __restrict__ count, int cap,
+                                                     float4* __restrict__ accum, int* work_counter, int* error_flag) {
+    const int n = min(*count, cap);
+    trace_persistent<SLAB, true>(sc, so, sd, n, work_counter, error_flag, [&](int ray, const HitRecord& h) {
+        if (h.prim == 0u) {
+            const float4 c = contrib[ray];
+            atomicAdd(&accum[__float_as_int(sd[ray].w)], make_float4(c.x, c.y, c.z, 0.0f));
+        }
+    });
+}
+
 // exact third barycentric of the winning triangle: e2 * inv_det of the same edge functions (pure function of ray + triangle)
 __device__ __forceinline__ float third_barycentric(const DeviceScene& sc, uint32_t prim, float3 o, float3 d) {
     const float4 A = __ldg(&sc.prims[3 * prim]);
@@ -47,21 +70,54 @@ __device__ __forceinline__ float third_barycentric(const DeviceScene& sc, uint32
 }
 
 template <class... Args>
-static void launch_extend(trace_ctx* c, int grid, Args... args) {
+static void launch_extend_plain(trace_ctx* c, int grid, Args... args) {
     c->kev_begin(0);
-    if (c->slab == 0) { if (c->count_nodes) k_wh_extend<0, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_extend<0, false><<<grid, 128, 0, c->stream>>>(args...); }
-    else if (c->slab == 2) { if (c->count_nodes) k_wh_extend<2, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_extend<2, false><<<grid, 128, 0, c->stream>>>(args...); }
-    else              { if (c->count_nodes) k_wh_extend<1, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_extend<1, false><<<grid, 128, 0, c->stream>>>(args...); }
+    if (c->slab == 0) { if (c->count_nodes) k_wh_extend<0, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_extend<0, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
+    else if (c->slab == 2) { if (c->count_nodes) k_wh_extend<2, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_extend<2, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
+    else              { if (c->count_nodes) k_wh_extend<1, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_extend<1, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
     c->stats.kernel_launches++;
     c->kev_end();
 }
 template <class... Args>
-static void launch_shadow(trace_ctx* c, int grid, Args... args) {
+static void launch_shadow_plain(trace_ctx* c, int grid, Args... args) {
     c->kev_begin(1);
-    if (c->slab == 0) { if (c->count_nodes) k_wh_shadow<0, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_shadow<0, false><<<grid, 128, 0, c->stream>>>(args...); }
-    else if (c->slab == 2) { if (c->count_nodes) k_wh_shadow<2, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_shadow<2, false><<<grid, 128, 0, c->stream>>>(args...); }
-    else              { if (c->count_nodes) k_wh_shadow<1, true><<<grid, 128, 0, c->stream>>>(args...); else k_wh_shadow<1, false><<<grid, 128, 0, c->stream>>>(args...); }
+    if (c->slab == 0) { if (c->count_nodes) k_wh_shadow<0, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_shadow<0, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
+    else if (c->slab == 2) { if (c->count_nodes) k_wh_shadow<2, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_shadow<2, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
+    else              { if (c->count_nodes) k_wh_shadow<1, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_shadow<1, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
     c->stats.kernel_launches++;
     c->kev_end();
 }
 
+
+static int* next_work_counter(trace_ctx* c) {
+    // int counter slots 64..127 are zeroed at the start of every batch / pass; one per traversal launch
+    int* p = ctx_icounters(c) + 64 + (c->work_slot % 64);
+    c->work_slot++;
+    return p;
+}
+static void launch_extend(trace_ctx* c, int grid, DeviceScene sc, const float4* ro, const float4* rd, const int* count, int cap,
+                          float4* hits, unsigned long long* counters, int* err) {
+    if (c->persist && !c->count_nodes && c->slab != 1) {
+        c->kev_begin(0);
+        int* wc = next_work_counter(c);
+        if (c->slab == 0) k_wh_extend_p<0><<<occupancy_grid(c, k_wh_extend_p<0>, 128), 128, 0, c->stream>>>(sc, ro, rd, count, cap, hits, wc, err);
+        else k_wh_extend_p<2><<<occupancy_grid(c, k_wh_extend_p<2>, 128), 128, 0, c->stream>>>(sc, ro, rd, count, cap, hits, wc, err);
+        c->stats.kernel_launches++;
+        c->kev_end();
+        return;
+    }
+    launch_extend_plain(c, grid, sc, ro, rd, count, cap, hits, counters, err);
+}
+static void launch_shadow(trace_ctx* c, int grid, DeviceScene sc, const float4* so, const float4* sd, const float4* contrib,
+                          const int* count, int cap, float4* accum, unsigned long long* counters, int* err) {
+    if (c->persist && !c->count_nodes && c->slab != 1) {
+        c->kev_begin(1);
+        int* wc = next_work_counter(c);
+        if (c->slab == 0) k_wh_shadow_p<0><<<occupancy_grid(c, k_wh_shadow_p<0>, 128), 128, 0, c->stream>>>(sc, so, sd, contrib, count, cap, accum, wc, err);
+        else k_wh_shadow_p<2><<<occupancy_grid(c, k_wh_shadow_p<2>, 128), 128, 0, c->stream>>>(sc, so, sd, contrib, count, cap, accum, wc, err);
+        c->stats.kernel_launches++;
+        c->kev_end();
+        return;
+    }
+    launch_shadow_plain(c, grid, sc, so, sd, contrib, count, cap, accum, counters, err);
+}
