@@ -89,6 +89,7 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "batch")) { if (v < 1024) return c->fail("batch too small"); c->batch = v; }
     else if (!strcmp(key, "count_nodes")) c->count_nodes = v != 0;
     else if (!strcmp(key, "persist")) c->persist = v != 0;
+    else if (!strcmp(key, "cap_percent")) { if (v < 100 || v > 1600) return c->fail("cap_percent must be in [100, 1600]"); c->cap_percent = (int)v; }
     else if (!strcmp(key, "time_kernels")) c->time_kernels = v != 0;
     else if (!strcmp(key, "rank")) c->rank = (int)v;
     else if (!strcmp(key, "world")) { if (v < 1) return c->fail("world must be >= 1"); c->world = (int)v; }

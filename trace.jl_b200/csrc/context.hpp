@@ -39,6 +39,7 @@ struct trace_ctx {
     int slab = 2;                 // 0 literal reference slab test, 1 textbook (not hit-equivalent), 2 guarded (default)
     int64_t batch = 1 << 26;      // camera samples per wavefront batch (queues: ~350 B per sample, allocated for min(batch, work))
     int count_nodes = 0;
+    int cap_percent = 200;        // ray-queue capacity per bounce level, in % of the batch size
     int persist = 0;              // persistent warps with dynamic ray fetch (measured slower on B200: kept as an option)
     int work_slot = 0;
     int time_kernels = 0;

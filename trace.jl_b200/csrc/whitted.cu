@@ -253,7 +253,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
         batch = (total_slots + nb - 1) / nb;
         batch = (batch + 255) / 256 * 256;
     }
-    const size_t cap_rays = (size_t)batch * 2;
+    const size_t cap_rays = (size_t)batch * (size_t)c->cap_percent / 100;
     const int shadow_mult = std::max(1, std::min(L.sc.n_lights, 4));
     const size_t cap_shadow = cap_rays * shadow_mult;
     L.cap_rays = (int)cap_rays; L.cap_shadow = (int)cap_shadow;
