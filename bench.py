@@ -181,9 +181,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    parts = {"render": 0.0, "reduce": 0.0, "n": 0}
+
+    def step(i, timed=False):
         film_dev.zero_()
-        D.render_whitted_sharded(ctx, scene, camera, spp, depth, 1000 + i, film_dev, rank, world)
+        if timed:
+            ev[0].record()
+        D.render_whitted_sharded(ctx, scene, camera, spp, depth, 1000 + i, film_dev, rank, world, reduce=False)
+        if timed:
+            ev[1].record()
+        if world > 1:
+            dist.reduce(film_dev, dst=0, op=dist.ReduceOp.SUM)
+        if timed:
+            ev[2].record()
+            torch.cuda.synchronize()
+            parts["render"] += ev[0].elapsed_time(ev[1]); parts["reduce"] += ev[1].elapsed_time(ev[2]); parts["n"] += 1
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps between barriers; max over ranks
     ctx.set_option("time_kernels", 1)
@@ -241,6 +254,18 @@ def main():
             roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "extend_traffic.json"))).get(args.workload)
         except Exception:
             pass
+
+    # ---- per-rank breakdown of a step (separate, untimed-for-the-metric pass): render vs film reduce
+    breakdown = None
+    if world > 1:
+        for i in range(3):
+            step(20_000 + i, timed=True)
+        bd = torch.tensor([parts["render"] / parts["n"], parts["reduce"] / parts["n"]], device=f"cuda:{local}")
+        bmax, bmin = bd.clone(), bd.clone()
+        dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bmin, op=dist.ReduceOp.MIN)
+        breakdown = {"render_ms_max_over_ranks": float(bmax[0]), "render_ms_min_over_ranks": float(bmin[0]),
+                     "reduce_ms_max_over_ranks": float(bmax[1]), "reduce_ms_min_over_ranks": float(bmin[1])}
 
     # ---- e2e: the reference-facing C ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
     host_film = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
@@ -327,7 +352,7 @@ def main():
                           "parallelism": f"tiles-rr{world}", "l2_policy": "inputs larger than L2 (ray queues + BVH > 126 MB per step)",
                           "rays_per_step": total_rays / args.steps},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-               "sppm": sppm}
+               "sppm": sppm, "breakdown": breakdown}
         print(json.dumps(out))
     ctx.close()
     if world > 1:

@@ -1,0 +1,105 @@
+"""Full-size GPU checks (-m gpu) at BASELINE.json's sizes, through size-independent properties (the oracle would take
+minutes there): tess-1M (999 840 triangles, 1920x1080) and the shadows SPPM scene at 1024x1024."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tess(T):
+    scene, camera, kw = T.scenes.tessellated()          # C3: 600^2 heightfield cells + two 266x264 UV spheres
+    assert scene.aggregate.n_primitives == 999_840
+    return scene, camera
+
+
+def test_tess1m_query_properties(T, ctx, tess):
+    scene, camera = tess
+    flat = ctx.upload(scene)
+    rng = np.random.default_rng(1)
+    n = 2_000_000
+    lo, hi = np.array(flat.nodes[0]["bmin"]), np.array(flat.nodes[0]["bmax"])
+    o = rng.uniform(lo - 5, hi + 5, (n, 3)).astype(np.float32)
+    d = (rng.uniform(lo, hi, (n, 3)) - o).astype(np.float32)
+    ctx.set_option("slab", 0)
+    p0, t0, b0 = ctx.intersect(o, d)
+    occ0 = ctx.occluded(o, d)
+    ctx.set_option("slab", 2)
+    p2, t2, b2 = ctx.intersect(o, d)
+    occ2 = ctx.occluded(o, d)
+    # guarded == literal, bit for bit
+    assert np.array_equal(p0, p2) and np.array_equal(t0.view(np.uint32), t2.view(np.uint32)) and np.array_equal(b0.view(np.uint32), b2.view(np.uint32))
+    assert np.array_equal(occ0, occ2)
+    # any-hit (t_max = Inf) <=> closest-hit found something
+    assert np.array_equal(occ2, p2 != 0)
+    hit = p2 != 0
+    assert 0.2 < hit.mean() < 1.0
+    # idempotence: re-tracing with t_max just beyond the hit finds the same primitive at the same t;
+    # with t_max just short of it, a different (farther-than-that) primitive can never be reported closer
+    tm = np.nextafter(t2[hit], np.float32(np.inf))
+    p3, t3, _ = ctx.intersect(o[hit], d[hit], tm)
+    assert np.array_equal(p3, p2[hit]) and np.array_equal(t3.view(np.uint32), t2[hit].view(np.uint32))
+    # barycentrics of triangle hits are a partition of unity (watertight test: all edge functions share a sign)
+    bb = b2[hit]
+    assert np.all(bb >= -1e-6) and np.all(bb.sum(1) <= 1 + 1e-5)
+    # original indices are valid and every reported t is positive
+    assert p2.max() <= 999_840 and np.all(t2[hit] > 0)
+
+
+def test_tess1m_whitted_linearity_and_weights(T, ctx, tess):
+    """Radiance is linear in the light intensity (x2 is exact in binary floating point up to atomic-add order), and the
+    filter-weight plane of the film depends on the camera samples only, not on the scene."""
+    scene, camera = tess
+    ctx.upload(scene)
+    cam, fd = camera.pod(), camera.film.desc()
+    a = np.zeros_like(camera.film.pixels)
+    ctx.reset_stats()
+    ctx.check(ctx.lib.trace_render_whitted(ctx.h, C.byref(cam), C.byref(fd), 2, 5, C.c_uint64(3), T._lib.ptr(a)))
+    st = ctx.stats()
+    assert st["rays_extend"] >= 1922 * 1082 * 2 and st["rays_shadow"] > 0 and st["queue_overflows"] == 0
+    assert np.isfinite(a).all() and float(a[..., 1].max()) > 0
+    # brighter light
+    scene2 = T.Scene([T.PointLight(scene.lights[0].light_to_world, T.RGBSpectrum(800.0))], scene.aggregate)
+    scene2._flat = None
+    ctx.upload(scene2)
+    b = np.zeros_like(a)
+    ctx.check(ctx.lib.trace_render_whitted(ctx.h, C.byref(cam), C.byref(fd), 2, 5, C.c_uint64(3), T._lib.ptr(b)))
+    assert np.allclose(b[..., :3], 2 * a[..., :3], rtol=1e-4, atol=1e-7)
+    assert np.allclose(b[..., 3], a[..., 3], rtol=1e-6)
+    # weights: every interior pixel received samples; each sample splats into at most (2r + 2)^2 = 16 pixels (Q4)
+    w = a[..., 3]
+    assert w[8:-8, 8:-8].min() > 0
+    # the film is accumulated into, never cleared (Q14)
+    ctx.check(ctx.lib.trace_render_whitted(ctx.h, C.byref(cam), C.byref(fd), 2, 5, C.c_uint64(3), T._lib.ptr(b)))
+    assert np.allclose(b[..., :3], 4 * a[..., :3], rtol=1e-4, atol=1e-7) and np.allclose(b[..., 3], 2 * w, rtol=1e-6)
+    ctx.upload(scene)
+
+
+def test_shadows_1024_sppm_properties(T, ctx):
+    """docs/code/spheres.jl at its shipped 1024x1024: radii only shrink, the image is finite and non-negative, and
+    photon sharding (2 halves into one flux buffer) equals the unsharded pass."""
+    from trace_jl_b200 import distributed as D
+    import torch
+    scene, camera, kw = T.scenes.shadows(resolution=1024)
+    sess = D.SPPMSession(ctx, scene, camera, kw["initial_search_radius"], kw["max_depth"])
+    assert sess.photons == 1023 * 1023
+    sess.step()
+    img1 = sess.image()
+    sess.step()
+    img2 = sess.image()
+    sess.close()
+    assert np.isfinite(img1).all() and np.isfinite(img2).all() and img1.min() >= 0 and img2.min() >= 0
+    assert float(img2.mean()) > 0.05
+    # sharded photon pass: iteration 1 traced as two halves must deposit the same flux (up to float-add order)
+    sess = D.SPPMSession(ctx, scene, camera, kw["initial_search_radius"], kw["max_depth"])
+    ctx.check(ctx.lib.trace_sppm_camera_pass(ctx.h, 1))
+    half = sess.photons // 2
+    ctx.check(ctx.lib.trace_sppm_photon_pass(ctx.h, 1, 0, half))
+    ctx.check(ctx.lib.trace_sppm_photon_pass(ctx.h, 1, half, sess.photons))
+    ctx.check(ctx.lib.trace_sppm_update(ctx.h))
+    sess.iteration = 1
+    img_sharded = sess.image()
+    sess.close()
+    assert np.allclose(img_sharded, img1, rtol=2e-4, atol=1e-6)
