@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--slab", type=int, default=2)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--persist", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=8)
     ap.add_argument("--ref-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sppm", action="store_true")
@@ -167,6 +168,7 @@ def main():
     ctx = T.Context(local, stream=stream)
     ctx.set_option("slab", args.slab)
     ctx.set_option("persist", args.persist)
+    ctx.set_option("lanes", args.lanes)
     if args.batch:
         ctx.set_option("batch", args.batch)
 
@@ -199,7 +201,7 @@ def main():
             parts["render"] += ev[0].elapsed_time(ev[1]); parts["reduce"] += ev[1].elapsed_time(ev[2]); parts["n"] += 1
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps between barriers; max over ranks
-    ctx.set_option("time_kernels", 1)
+    ctx.set_option("time_kernels", 0)
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -227,7 +229,23 @@ def main():
     value = total_rays / (ms_total * 1e-3) / 1e6
     launches = int(rays[2].item())
 
-    # ---- roofline of the dominant kernel (closest-hit `extend`): algorithmic bytes / CUDA-event launch time
+    # ---- roofline of the dominant kernel (closest-hit `extend`): algorithmic bytes / CUDA-event launch time.
+    # In the timed region above up to `lanes` sub-batches run concurrently on side streams, so per-kernel event times
+    # overlap; the per-launch durations are therefore taken in a second timed pass of the same K steps with lanes = 1
+    # (kernels back to back on one stream), CUDA events around every extend / shadow launch.
+    ctx.set_option("lanes", 1)
+    ctx.set_option("time_kernels", 1)
+    step(5_000)
+    barrier()
+    ctx.reset_stats()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for i in range(args.steps):
+        step(5_001 + i)
+    r1.record()
+    barrier()
+    serial_ms = r0.elapsed_time(r1)
+    st = ctx.stats()
     ext_ms, ext_n = st["ms_extend"], max(1, st["extend_launches"])
     ctx.set_option("time_kernels", 0)
     ctx.set_option("count_nodes", 1)
@@ -236,6 +254,7 @@ def main():
     torch.cuda.synchronize()
     sc = ctx.stats()
     ctx.set_option("count_nodes", 0)
+    ctx.set_option("lanes", args.lanes)
     n_rays_cnt = max(1, sc["rays_extend"] + sc["rays_shadow"])
     nodes_per_ray = sc["nodes_visited"] / n_rays_cnt
     prims_per_ray = sc["prims_tested"] / n_rays_cnt
@@ -247,7 +266,9 @@ def main():
                 "kernel": "k_wh_extend", "peak_source": f"of {peak_kind}", "avg_launch_ms": ext_ms / ext_n,
                 "launches_timed": int(ext_n), "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                 "prims_per_ray": prims_per_ray, "extend_Mrays_per_s": ext_rays / max(1e-9, ext_ms * 1e-3) / 1e6,
-                "extend_share_of_step": ext_ms / max(1e-9, ms_total) if world == 1 else None,
+                "extend_share_of_step": ext_ms / max(1e-9, serial_ms), "serial_pass_ms_per_step": serial_ms / args.steps,
+                "shadow_avg_launch_ms": st["ms_shadow"] / max(1, st["shadow_launches"]),
+                "shadow_share_of_step": st["ms_shadow"] / max(1e-9, serial_ms),
                 "note": "traversal is L1/L2-latency bound: algorithmic bytes are mostly cache hits, not HBM traffic"}
     if os.path.exists(os.path.join(ROOT, "profiles", "extend_traffic.json")):
         try:
@@ -349,7 +370,7 @@ def main():
                "config": {"workload": f"whitted-{args.workload}", "spp": spp, "max_depth": depth,
                           "resolution": list(WORKLOADS[args.workload][0]["res"]), "triangles": int(scene.aggregate.n_primitives),
                           "bvh_nodes": int(len(flat.nodes)), "slab_test": {0: "literal (bounds.jl:180-200)", 1: "textbook (not hit-equivalent)", 2: "guarded (literal AND conservative interval; hit-identical, tests/test_gpu_parity.py)"}[args.slab],
-                          "parallelism": f"tiles-rr{world}", "l2_policy": "inputs larger than L2 (ray queues + BVH > 126 MB per step)",
+                          "parallelism": f"tiles-rr{world}", "lanes": args.lanes, "l2_policy": "inputs larger than L2 (ray queues + BVH > 126 MB per step)",
                           "rays_per_step": total_rays / args.steps},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                "sppm": sppm, "breakdown": breakdown}

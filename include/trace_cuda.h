@@ -150,7 +150,8 @@ const char* trace_last_error(const trace_ctx* ctx);
 /* options: "slab" 0 = literal reference slab test (bounds.jl:180-200), 1 = textbook slab (measured only: not
  *          hit-equivalent), 2 = guarded: literal AND a conservative interval test, hit-identical to 0 (default 2);
  *          "batch" camera samples per wavefront batch; "cap_percent" ray-queue capacity per bounce level in % of the
- *          batch (default 200; an overflowing batch is re-run in halves); "persist" 0/1 persistent-warp traversal
+ *          batch (default 200; an overflowing batch is re-run in halves); "lanes" sub-batches of a Whitted render in
+ *          flight concurrently on side streams (default 8); "persist" 0/1 persistent-warp traversal
  *          kernels (default 0); "count_nodes" 0/1; "time_kernels" 0/1;
  *          "rank"/"world" shard selection for renders (tiles / photons). */
 int         trace_set_option(trace_ctx* ctx, const char* key, int64_t value);

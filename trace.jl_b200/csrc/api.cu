@@ -52,7 +52,12 @@ extern "C" int trace_create(trace_ctx** out, int device, void* cuda_stream) {
     }
     bool ok = cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess &&
               cudaEventCreate(&c->evk0) == cudaSuccess && cudaEventCreate(&c->evk1) == cudaSuccess;
-    ok = ok && c->b_counters.ensure(TR_INT_COUNTERS * sizeof(int) + ST_COUNT * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && c->b_counters.ensure(ctx_counter_bytes()) == cudaSuccess;
+    c->cur_stream = c->stream;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int l = 0; l < trace_ctx::MAX_LANES && ok; ++l)
+        ok = cudaStreamCreateWithFlags(&c->side[l], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&c->h_flags, 64 * sizeof(int)) == cudaSuccess;
     if (ok) ok = cudaMemsetAsync(c->b_counters.p, 0, c->b_counters.bytes, c->stream) == cudaSuccess;
     if (!ok) { trace_destroy(c); return 5; }
@@ -72,6 +77,8 @@ extern "C" void trace_destroy(trace_ctx* c) {
     for (auto& b : c->b_queue) b.release();
     for (auto& b : c->b_misc) b.release();
     for (auto& e : c->kev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (int l = 0; l < trace_ctx::MAX_LANES; ++l) { if (c->side[l]) cudaStreamDestroy(c->side[l]); if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -89,6 +96,7 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "batch")) { if (v < 1024) return c->fail("batch too small"); c->batch = v; }
     else if (!strcmp(key, "count_nodes")) c->count_nodes = v != 0;
     else if (!strcmp(key, "persist")) c->persist = v != 0;
+    else if (!strcmp(key, "lanes")) { if (v < 1 || v > trace_ctx::MAX_LANES) return c->fail("lanes must be in [1, 16]"); c->lanes = (int)v; }
     else if (!strcmp(key, "cap_percent")) { if (v < 100 || v > 1600) return c->fail("cap_percent must be in [100, 1600]"); c->cap_percent = (int)v; }
     else if (!strcmp(key, "time_kernels")) c->time_kernels = v != 0;
     else if (!strcmp(key, "rank")) c->rank = (int)v;

@@ -32,6 +32,14 @@ struct trace_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // lanes: independent sub-batches of a render run concurrently on side streams (each with its own queues and
+    // counter block) so that one lane's latency-bound deep-bounce launches overlap another lane's wide ones
+    static const int MAX_LANES = 16;
+    cudaStream_t side[MAX_LANES] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {};
+    cudaStream_t cur_stream = nullptr;      // stream the launch helpers enqueue on (== stream outside a laned render)
+    int cur_lane = 0;
+    int lanes = 8;
     int num_sms = 148;
     std::string err;
 
@@ -67,11 +75,11 @@ struct trace_ctx {
         if (!time_kernels) return;
         if (kev_used == kev.size()) { KernelEvent e; cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.kind = kind; kev.push_back(e); }
         kev[kev_used].kind = kind;
-        cudaEventRecord(kev[kev_used].a, stream);
+        cudaEventRecord(kev[kev_used].a, cur_stream);
     }
     void kev_end() {
         if (!time_kernels) return;
-        cudaEventRecord(kev[kev_used].b, stream);
+        cudaEventRecord(kev[kev_used].b, cur_stream);
         kev_used++;
     }
     void kev_collect() {      // call after the stream has been synchronised
@@ -110,7 +118,17 @@ static const int TR_INT_COUNTERS = 128;    // ints at the start of b_counters (6
 // int counter slots
 enum { IC_OVERFLOW = 60, IC_ERROR = 61 };
 
-inline int* ctx_icounters(trace_ctx* c) { return c->b_counters.as<int>(); }
+// b_counters layout: [lane 0 ints][u64 stats][lane 1 ints][lane 2 ints]...
+inline size_t ctx_counter_bytes() {
+    return TR_INT_COUNTERS * sizeof(int) * trace_ctx::MAX_LANES + ST_COUNT * sizeof(unsigned long long);
+}
+inline int* ctx_icounters_lane(trace_ctx* c, int lane) {
+    char* base = c->b_counters.as<char>();
+    if (lane == 0) return reinterpret_cast<int*>(base);
+    return reinterpret_cast<int*>(base + TR_INT_COUNTERS * sizeof(int) + ST_COUNT * sizeof(unsigned long long) +
+                                  (size_t)(lane - 1) * TR_INT_COUNTERS * sizeof(int));
+}
+inline int* ctx_icounters(trace_ctx* c) { return ctx_icounters_lane(c, c->cur_lane); }
 inline unsigned long long* ctx_stats64(trace_ctx* c) {
     return reinterpret_cast<unsigned long long*>(c->b_counters.as<char>() + TR_INT_COUNTERS * sizeof(int));
 }

@@ -72,18 +72,18 @@ __device__ __forceinline__ float third_barycentric(const DeviceScene& sc, uint32
 template <class... Args>
 static void launch_extend_plain(trace_ctx* c, int grid, Args... args) {
     c->kev_begin(0);
-    if (c->slab == 0) { if (c->count_nodes) k_wh_extend<0, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_extend<0, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
-    else if (c->slab == 2) { if (c->count_nodes) k_wh_extend<2, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_extend<2, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
-    else              { if (c->count_nodes) k_wh_extend<1, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_extend<1, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
+    if (c->slab == 0) { if (c->count_nodes) k_wh_extend<0, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_extend<0, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
+    else if (c->slab == 2) { if (c->count_nodes) k_wh_extend<2, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_extend<2, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
+    else              { if (c->count_nodes) k_wh_extend<1, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_extend<1, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
     c->stats.kernel_launches++;
     c->kev_end();
 }
 template <class... Args>
 static void launch_shadow_plain(trace_ctx* c, int grid, Args... args) {
     c->kev_begin(1);
-    if (c->slab == 0) { if (c->count_nodes) k_wh_shadow<0, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_shadow<0, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
-    else if (c->slab == 2) { if (c->count_nodes) k_wh_shadow<2, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_shadow<2, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
-    else              { if (c->count_nodes) k_wh_shadow<1, true><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); else k_wh_shadow<1, false><<<persistent_grid(c, 16), 128, 0, c->stream>>>(args...); }
+    if (c->slab == 0) { if (c->count_nodes) k_wh_shadow<0, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_shadow<0, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
+    else if (c->slab == 2) { if (c->count_nodes) k_wh_shadow<2, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_shadow<2, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
+    else              { if (c->count_nodes) k_wh_shadow<1, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_shadow<1, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
     c->stats.kernel_launches++;
     c->kev_end();
 }
@@ -100,8 +100,8 @@ static void launch_extend(trace_ctx* c, int grid, DeviceScene sc, const float4* 
     if (c->persist && !c->count_nodes && c->slab != 1) {
         c->kev_begin(0);
         int* wc = next_work_counter(c);
-        if (c->slab == 0) k_wh_extend_p<0><<<occupancy_grid(c, k_wh_extend_p<0>, 128), 128, 0, c->stream>>>(sc, ro, rd, count, cap, hits, wc, err);
-        else k_wh_extend_p<2><<<occupancy_grid(c, k_wh_extend_p<2>, 128), 128, 0, c->stream>>>(sc, ro, rd, count, cap, hits, wc, err);
+        if (c->slab == 0) k_wh_extend_p<0><<<occupancy_grid(c, k_wh_extend_p<0>, 128), 128, 0, c->cur_stream>>>(sc, ro, rd, count, cap, hits, wc, err);
+        else k_wh_extend_p<2><<<occupancy_grid(c, k_wh_extend_p<2>, 128), 128, 0, c->cur_stream>>>(sc, ro, rd, count, cap, hits, wc, err);
         c->stats.kernel_launches++;
         c->kev_end();
         return;
@@ -113,8 +113,8 @@ static void launch_shadow(trace_ctx* c, int grid, DeviceScene sc, const float4* 
     if (c->persist && !c->count_nodes && c->slab != 1) {
         c->kev_begin(1);
         int* wc = next_work_counter(c);
-        if (c->slab == 0) k_wh_shadow_p<0><<<occupancy_grid(c, k_wh_shadow_p<0>, 128), 128, 0, c->stream>>>(sc, so, sd, contrib, count, cap, accum, wc, err);
-        else k_wh_shadow_p<2><<<occupancy_grid(c, k_wh_shadow_p<2>, 128), 128, 0, c->stream>>>(sc, so, sd, contrib, count, cap, accum, wc, err);
+        if (c->slab == 0) k_wh_shadow_p<0><<<occupancy_grid(c, k_wh_shadow_p<0>, 128), 128, 0, c->cur_stream>>>(sc, so, sd, contrib, count, cap, accum, wc, err);
+        else k_wh_shadow_p<2><<<occupancy_grid(c, k_wh_shadow_p<2>, 128), 128, 0, c->cur_stream>>>(sc, so, sd, contrib, count, cap, accum, wc, err);
         c->stats.kernel_launches++;
         c->kev_end();
         return;

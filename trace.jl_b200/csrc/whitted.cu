@@ -175,7 +175,7 @@ __global__ void k_wh_batch_stats(int* counters, unsigned long long* stats, int m
         if (batch_flag) *batch_flag = counters[IC_OVERFLOW];
         unsigned long long e = 0, s = 0;
         for (int l = 1; l <= max_depth; ++l) { e += min(counters[l], cap_rays); s += min(counters[32 + l], cap_shadow); }
-        if (!counters[IC_OVERFLOW]) { stats[ST_RAYS_EXTEND] += e; stats[ST_RAYS_SHADOW] += s; }
+        if (!counters[IC_OVERFLOW]) { atomicAdd(&stats[ST_RAYS_EXTEND], e); atomicAdd(&stats[ST_RAYS_SHADOW], s); }
     }
 }
 
@@ -189,31 +189,31 @@ static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long 
     L.n_slots = (int)count;
     int* ic = ctx_icounters(c);
     unsigned long long* st = ctx_stats64(c);
-    TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->stream));
-    TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), c->stream)); c->work_slot = 0;
-    TR_CUDA(c, cudaMemsetAsync(ic + IC_OVERFLOW, 0, sizeof(int), c->stream));
+    TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->cur_stream));
+    TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), c->cur_stream)); c->work_slot = 0;
+    TR_CUDA(c, cudaMemsetAsync(ic + IC_OVERFLOW, 0, sizeof(int), c->cur_stream));
     const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
-    k_wh_generate<<<g_stream, 256, 0, c->stream>>>(L);
+    k_wh_generate<<<g_stream, 256, 0, c->cur_stream>>>(L);
     c->stats.kernel_launches++;
     for (int level = 1; level <= L.max_depth; ++level) {
         const int cur = (level - 1) & 1;
         launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap_rays,
                       L.hits, st + ST_NODES, ic + IC_ERROR);
-        k_wh_shade<<<occupancy_grid(c, k_wh_shade, 128), 128, 0, c->stream>>>(L, level);
+        k_wh_shade<<<occupancy_grid(c, k_wh_shade, 128), 128, 0, c->cur_stream>>>(L, level);
         c->stats.kernel_launches++;
         launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
                       (const int*)(ic + 32 + level), L.cap_shadow, L.accum, st + ST_NODES, ic + IC_ERROR);
     }
-    k_wh_splat<<<g_stream, 256, 0, c->stream>>>(L);
-    k_wh_batch_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap_rays, L.cap_shadow, batch_flag);
+    k_wh_splat<<<g_stream, 256, 0, c->cur_stream>>>(L);
+    k_wh_batch_stats<<<1, 32, 0, c->cur_stream>>>(ic, st, L.max_depth, L.cap_rays, L.cap_shadow, batch_flag);
     c->stats.kernel_launches += 2;
     TR_CUDA(c, cudaGetLastError());
     if (batch_flag) return 0;
-    TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ic + IC_OVERFLOW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ic + IC_OVERFLOW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->cur_stream));
+    TR_CUDA(c, cudaStreamSynchronize(c->cur_stream));
     c->kev_collect();
     if (c->h_flags[1]) {
-        cudaMemsetAsync(ic + IC_ERROR, 0, sizeof(int), c->stream);
+        cudaMemsetAsync(ic + IC_ERROR, 0, sizeof(int), c->cur_stream);
         return c->fail("traversal stack overflow (more than 64 pending nodes; the reference would throw a BoundsError, bvh.jl:222)");
     }
     if (c->h_flags[0]) {                                  // a queue overflowed: nothing was splatted, redo in halves
@@ -244,59 +244,82 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
     L.tiles = c->b_misc[1].as<int>();
     const long long total_slots = (long long)tiles.size() * 256 * spp;
-    // batches of (at most) c->batch samples, evened out; deep bounce levels hold few but expensive rays, so large
-    // batches keep those launches full (measured on B200: 2M-sample batches 58 ms/step, 8M 49 ms on tess-1M)
-    long long batch = std::min<long long>(c->batch, total_slots);
-    if (batch < 1) batch = 1;
-    {
-        const long long nb = (total_slots + batch - 1) / batch;
-        batch = (total_slots + nb - 1) / nb;
-        batch = (batch + 255) / 256 * 256;
-    }
+    // batches of (at most) c->batch samples, evened out.  Deep bounce levels hold few but expensive rays (a launch
+    // cannot end before its slowest ray: ~0.2 ms for a 1000-node walk), so batches are large and up to `lanes` of them
+    // run concurrently on side streams, each lane with its own queues and counters.
+    long long nb = std::max<long long>(1, (total_slots + c->batch - 1) / c->batch);
+    int K = 1;
+    if (total_slots >= (long long)c->lanes * 131072) { K = c->lanes; nb = std::max<long long>(nb, K); }
+    long long batch = (total_slots + nb - 1) / nb;
+    batch = std::max<long long>(256, (batch + 255) / 256 * 256);
+    nb = (total_slots + batch - 1) / batch;
     const size_t cap_rays = (size_t)batch * (size_t)c->cap_percent / 100;
     const int shadow_mult = std::max(1, std::min(L.sc.n_lights, 4));
     const size_t cap_shadow = cap_rays * shadow_mult;
     L.cap_rays = (int)cap_rays; L.cap_shadow = (int)cap_shadow;
-    for (int k = 0; k < 6; ++k) TR_CUDA(c, c->b_queue[k].ensure(cap_rays * sizeof(float4)));
-    TR_CUDA(c, c->b_queue[6].ensure(cap_rays * sizeof(float4)));
-    for (int k = 7; k < 10; ++k) TR_CUDA(c, c->b_queue[k].ensure(cap_shadow * sizeof(float4)));
-    TR_CUDA(c, c->b_queue[10].ensure((size_t)batch * sizeof(float4)));
-    TR_CUDA(c, c->b_queue[11].ensure((size_t)batch * sizeof(float2)));
+    for (int k = 0; k < 7; ++k) TR_CUDA(c, c->b_queue[k].ensure(K * cap_rays * sizeof(float4)));
+    for (int k = 7; k < 10; ++k) TR_CUDA(c, c->b_queue[k].ensure(K * cap_shadow * sizeof(float4)));
+    TR_CUDA(c, c->b_queue[10].ensure((size_t)K * batch * sizeof(float4)));
+    TR_CUDA(c, c->b_queue[11].ensure((size_t)K * batch * sizeof(float2)));
     const size_t npix = (size_t)L.film.width * L.film.height;
     TR_CUDA(c, c->b_queue[12].ensure(npix * sizeof(float4)));
-    L.ro[0] = c->b_queue[0].as<float4>(); L.ro[1] = c->b_queue[1].as<float4>();
-    L.rd[0] = c->b_queue[2].as<float4>(); L.rd[1] = c->b_queue[3].as<float4>();
-    L.rw[0] = c->b_queue[4].as<float4>(); L.rw[1] = c->b_queue[5].as<float4>();
-    L.hits = c->b_queue[6].as<float4>();
-    L.so = c->b_queue[7].as<float4>(); L.sd = c->b_queue[8].as<float4>(); L.sc_contrib = c->b_queue[9].as<float4>();
-    L.accum = c->b_queue[10].as<float4>(); L.filmpos = c->b_queue[11].as<float2>();
     L.film_rgbw = c->b_queue[12].as<float4>();
-    L.counters = ctx_icounters(c);
+    std::vector<WhittedLaunch> lane((size_t)K, L);
+    for (int l = 0; l < K; ++l) {
+        WhittedLaunch& W = lane[l];
+        W.ro[0] = c->b_queue[0].as<float4>() + l * cap_rays; W.ro[1] = c->b_queue[1].as<float4>() + l * cap_rays;
+        W.rd[0] = c->b_queue[2].as<float4>() + l * cap_rays; W.rd[1] = c->b_queue[3].as<float4>() + l * cap_rays;
+        W.rw[0] = c->b_queue[4].as<float4>() + l * cap_rays; W.rw[1] = c->b_queue[5].as<float4>() + l * cap_rays;
+        W.hits = c->b_queue[6].as<float4>() + l * cap_rays;
+        W.so = c->b_queue[7].as<float4>() + l * cap_shadow; W.sd = c->b_queue[8].as<float4>() + l * cap_shadow;
+        W.sc_contrib = c->b_queue[9].as<float4>() + l * cap_shadow;
+        W.accum = c->b_queue[10].as<float4>() + (size_t)l * batch; W.filmpos = c->b_queue[11].as<float2>() + (size_t)l * batch;
+        W.counters = ctx_icounters_lane(c, l);
+    }
     TR_CUDA(c, cudaMemsetAsync(L.film_rgbw, 0, npix * sizeof(float4), c->stream));
     TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    const int n_batches = (int)((total_slots + batch - 1) / batch);
-    TR_CUDA(c, c->b_misc[2].ensure((size_t)(n_batches + 1) * sizeof(int)));
+    TR_CUDA(c, c->b_misc[2].ensure((size_t)(nb + 1) * sizeof(int)));
     int* d_flags = c->b_misc[2].as<int>();
-    for (int bi = 0; bi < n_batches; ++bi) {
-        const long long b = (long long)bi * batch;
-        if (run_batch(c, L, b, std::min(batch, total_slots - b), 0, d_flags + bi)) return 1;
+    if (K > 1) {
+        TR_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+        for (int l = 0; l < K; ++l) TR_CUDA(c, cudaStreamWaitEvent(c->side[l], c->ev_fork, 0));
     }
+    int rc = 0;
+    for (long long bi = 0; bi < nb && !rc; ++bi) {
+        const int l = (int)(bi % K);
+        c->cur_lane = l;
+        c->cur_stream = K > 1 ? c->side[l] : c->stream;
+        const long long b = bi * batch;
+        rc = run_batch(c, lane[l], b, std::min(batch, total_slots - b), 0, d_flags + bi);
+    }
+    if (K > 1) {
+        for (int l = 0; l < K; ++l) {
+            cudaEventRecord(c->ev_join[l], c->side[l]);
+            cudaStreamWaitEvent(c->stream, c->ev_join[l], 0);
+        }
+    }
+    c->cur_lane = 0;
+    c->cur_stream = c->stream;
+    if (rc) return 1;
     {
-        std::vector<int> h_flags((size_t)n_batches + 2, 0);
-        TR_CUDA(c, cudaMemcpyAsync(h_flags.data(), d_flags, (size_t)n_batches * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ctx_icounters(c) + IC_OVERFLOW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<int> h_flags((size_t)nb + 2, 0), h_err((size_t)K, 0);
+        TR_CUDA(c, cudaMemcpyAsync(h_flags.data(), d_flags, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        for (int l = 0; l < K; ++l)
+            TR_CUDA(c, cudaMemcpyAsync(&h_err[l], ctx_icounters_lane(c, l) + IC_ERROR, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         TR_CUDA(c, cudaStreamSynchronize(c->stream));
         c->kev_collect();
-        if (c->h_flags[1]) {
-            cudaMemsetAsync(ctx_icounters(c) + IC_ERROR, 0, sizeof(int), c->stream);
-            return c->fail("traversal stack overflow (more than 64 pending nodes; the reference would throw a BoundsError, bvh.jl:222)");
+        for (int l = 0; l < K; ++l) {
+            if (h_err[l]) {
+                cudaMemsetAsync(ctx_icounters_lane(c, l) + IC_ERROR, 0, sizeof(int), c->stream);
+                return c->fail("traversal stack overflow (more than 64 pending nodes; the reference would throw a BoundsError, bvh.jl:222)");
+            }
         }
-        for (int bi = 0; bi < n_batches; ++bi) {
+        for (long long bi = 0; bi < nb; ++bi) {
             if (!h_flags[bi]) continue;                     // overflowed batches were not splatted: redo them in halves
             c->stats.queue_overflows++;
-            const long long b = (long long)bi * batch, cnt = std::min(batch, total_slots - b), half = cnt / 2;
+            const long long b = bi * batch, cnt = std::min(batch, total_slots - b), half = cnt / 2;
             if (cnt < 2048) return c->fail("ray queue overflow that halving the batch cannot resolve");
-            if (run_batch(c, L, b, half, 1) || run_batch(c, L, b + half, cnt - half, 1)) return 1;
+            if (run_batch(c, lane[0], b, half, 1) || run_batch(c, lane[0], b + half, cnt - half, 1)) return 1;
         }
     }
     k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix);
