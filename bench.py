@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--slab", type=int, default=2)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--persist", type=int, default=0)
-    ap.add_argument("--lanes", type=int, default=8)
+    ap.add_argument("--lanes", type=int, default=12)
     ap.add_argument("--ref-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sppm", action="store_true")

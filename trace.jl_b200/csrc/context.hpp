@@ -39,7 +39,7 @@ struct trace_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {};
     cudaStream_t cur_stream = nullptr;      // stream the launch helpers enqueue on (== stream outside a laned render)
     int cur_lane = 0;
-    int lanes = 8;
+    int lanes = 12;
     int num_sms = 148;
     std::string err;
 

@@ -38,6 +38,7 @@ struct SppmLaunch {
     // grid
     GridParams* grid;
     unsigned int *cell_start, *cell_cursor, *cell_items;
+    float4* cell_vp;           // {p, r^2} of each CSR entry, in list order: candidate tests stream 16 B coalesced
     unsigned int items_cap;
     // queues
     float4 *ro[2], *rd[2], *rw[2], *hits;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) k_grid_insert(SppmLaunch L) {
             if (!FILL) atomicAdd(&L.cell_start[h], 1u);
             else {
                 const unsigned int slot = atomicAdd(&L.cell_cursor[h], 1u);
-                if (slot < L.items_cap) L.cell_items[slot] = (unsigned int)pix;
+                if (slot < L.items_cap) { L.cell_items[slot] = (unsigned int)pix; L.cell_vp[slot] = make_float4(A.x, A.y, A.z, A.w); }
             }
         }
     }
@@ -365,21 +366,26 @@ __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
 // (Phi, M) with one 128-bit vector atomic.  Lists are long where visible points are dense (cell edge ~ max radius,
 // pixel footprint << radius: thousands of entries per cell), so a thread-per-photon loop serialises on its longest
 // list; a warp per request keeps every lane busy and the loads coalesced.
+#define TR_DEPOSIT_SPLIT 8
 __global__ void __launch_bounds__(128) k_photon_deposit(SppmLaunch L, int level) {
     const int n = min(L.counters[32 + level], L.cap);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     unsigned int deposits = 0;
-    for (int r = warp; r < n; r += n_warps) {
+    // TR_DEPOSIT_SPLIT warps share one request (interleaved 32-entry slices of its list): a request's chain of
+    // dependent gathers is 8x shorter and there are 8x more independent tasks to hide latency with
+    const long long n_tasks = (long long)n * TR_DEPOSIT_SPLIT;
+    for (long long task = warp; task < n_tasks; task += n_warps) {
+        const int r = (int)(task / TR_DEPOSIT_SPLIT), sub = (int)(task % TR_DEPOSIT_SPLIT);
         const float4 P = L.so[r], WO = L.sd[r], B = L.sc_contrib[r];
         const float3 p = xyz(P), wo = xyz(WO), beta = xyz(B);
         const unsigned int hsh = __float_as_uint(P.w);
         const unsigned int e0 = L.cell_start[hsh], e1 = L.cell_start[hsh + 1];
-        for (unsigned int e = e0 + lane; e < e1; e += 32) {
-            const unsigned int pix = L.cell_items[e];
-            const float4 A = L.vpA[pix];
+        for (unsigned int e = e0 + sub * 32 + lane; e < e1; e += 32 * TR_DEPOSIT_SPLIT) {
+            const float4 A = __ldcs(&L.cell_vp[e]);                  // streamed once per request: keep it out of L1
             const float3 dd = xyz(A) - p;
             if (dot3(dd, dd) > A.w) continue;
+            const unsigned int pix = L.cell_items[e];
             const float4 Bv = L.vpB[pix];
             Frame vf;
             vf.ns = xyz(L.vpC[pix]); vf.ss = xyz(L.vpD[pix]); vf.ng = xyz(L.vpE[pix]);
@@ -453,7 +459,7 @@ __global__ void k_sppm_stats(int* counters, unsigned long long* stats, int max_d
 // ---------------------------------------------------------------- host side
 struct SppmState {
     SppmLaunch L;
-    DevBuf pix[10], grid, cells[3], scan_sums, q[10], table, lights;
+    DevBuf pix[10], grid, cells[4], scan_sums, q[10], table, lights;
     float r0;
     int photon_cap;
     bool active = false;
@@ -514,6 +520,8 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     TR_CUDA(c, s->cells[0].ensure((np + 1) * sizeof(unsigned int)));
     TR_CUDA(c, s->cells[1].ensure((np + 1) * sizeof(unsigned int)));
     TR_CUDA(c, s->cells[2].ensure((size_t)L.items_cap * sizeof(unsigned int)));
+    TR_CUDA(c, s->cells[3].ensure((size_t)L.items_cap * sizeof(float4)));
+    L.cell_vp = s->cells[3].as<float4>();
     L.cell_start = s->cells[0].as<unsigned int>(); L.cell_cursor = s->cells[1].as<unsigned int>();
     L.cell_items = s->cells[2].as<unsigned int>();
     const int scan_blocks = (int)((np + 1 + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS));
