@@ -45,6 +45,7 @@ struct SppmLaunch {
     float4 *so, *sd, *sc_contrib;
     int* counters;
     int cap;
+    int cap_shadow;            // shadow-ray queue (camera pass) / deposit-request queue (photon pass): all levels share it
     // photons
     long long photon_begin;    // first photon index (within the iteration) of this launch
     int n_photons;
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level)
                 if (!is_black3(f)) {
                     const float3 contrib = ((f * Li) / 1.0f) / light_pdf;
                     const float3 sdir = lpos - it.p;
-                    const int q = queue_claim(&L.counters[32 + level]);
+                    const int q = queue_claim(&L.counters[32]);
+                    if (q >= L.cap_shadow) { L.counters[IC_OVERFLOW] = 1; continue; }
                     L.so[q] = f4(it.p + 1e-6f * sdir, TR_INF);
                     L.sd[q] = f4(sdir, __int_as_float(pix));
                     L.sc_contrib[q] = f4(contrib, 0.0f);
@@ -334,7 +336,8 @@ __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
             if (g.valid && to_grid(g, it.p, cell)) {
                 const unsigned int hsh = grid_hash(cell[0], cell[1], cell[2], (unsigned int)L.npix);
                 if (L.cell_start[hsh + 1] > L.cell_start[hsh]) {
-                    const int q = queue_claim(&L.counters[32 + level]);
+                    const int q = queue_claim(&L.counters[32]);
+                    if (q >= L.cap_shadow) { L.counters[IC_OVERFLOW] = 1; continue; }
                     L.so[q] = f4(it.p, __uint_as_float(hsh));
                     L.sd[q] = f4(wo, 0.0f);
                     L.sc_contrib[q] = f4(beta, 0.0f);
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
 // list; a warp per request keeps every lane busy and the loads coalesced.
 #define TR_DEPOSIT_SPLIT 8
 __global__ void __launch_bounds__(128) k_photon_deposit(SppmLaunch L, int level) {
-    const int n = min(L.counters[32 + level], L.cap);
+    const int n = min(L.counters[32], L.cap_shadow);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     unsigned int deposits = 0;
@@ -450,7 +453,8 @@ __global__ void k_sppm_init(SppmLaunch L, float r0) {
 __global__ void k_sppm_stats(int* counters, unsigned long long* stats, int max_depth, int cap, int count_shadow) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long e = 0, s = 0;
-        for (int l = 1; l <= max_depth; ++l) { e += min(counters[l], cap); s += counters[32 + l]; }
+        for (int l = 1; l <= max_depth; ++l) e += min(counters[l], cap);
+        s = counters[32];
         stats[ST_RAYS_EXTEND] += e;
         if (count_shadow) stats[ST_RAYS_SHADOW] += s;      // in the photon pass slots 32.. count deposit requests
     }
@@ -530,7 +534,9 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     s->photon_cap = (int)std::min<int64_t>(photons, std::max<int64_t>(c->batch * 2, 1 << 20));
     const size_t cap = std::max<size_t>(np, (size_t)s->photon_cap);
     L.cap = (int)cap;
-    for (int k = 0; k < 10; ++k) TR_CUDA(c, s->q[k].ensure(cap * sizeof(float4)));
+    L.cap_shadow = (int)std::min<size_t>(cap * (size_t)max_depth, (size_t)1 << 30);
+    for (int k = 0; k < 7; ++k) TR_CUDA(c, s->q[k].ensure(cap * sizeof(float4)));
+    for (int k = 7; k < 10; ++k) TR_CUDA(c, s->q[k].ensure((size_t)L.cap_shadow * sizeof(float4)));
     L.ro[0] = s->q[0].as<float4>(); L.ro[1] = s->q[1].as<float4>(); L.rd[0] = s->q[2].as<float4>(); L.rd[1] = s->q[3].as<float4>();
     L.rw[0] = s->q[4].as<float4>(); L.rw[1] = s->q[5].as<float4>(); L.hits = s->q[6].as<float4>();
     L.so = s->q[7].as<float4>(); L.sd = s->q[8].as<float4>(); L.sc_contrib = s->q[9].as<float4>();
@@ -591,9 +597,10 @@ extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
                       st + ST_NODES, ic + IC_ERROR);
         k_sppm_cam_shade<<<occupancy_grid(c, k_sppm_cam_shade, 128), 128, 0, c->stream>>>(L, level);
         c->stats.kernel_launches++;
-        launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
-                      (const int*)(ic + 32 + level), L.cap, L.Ld, st + ST_NODES, ic + IC_ERROR);
     }
+    // shadow rays of all levels in one any-hit launch (they only feed Ld)
+    launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
+                  (const int*)(ic + 32), L.cap_shadow, L.Ld, st + ST_NODES, ic + IC_ERROR);
     k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap, 1);
     // hash grid of the visible points: bounds -> resolution -> count -> scan -> fill
     const int n_cells = L.npix + 1;
@@ -637,11 +644,10 @@ extern "C" int trace_sppm_photon_pass(trace_ctx* c, int iteration, int64_t begin
                           st + ST_NODES, ic + IC_ERROR);
             k_photon_shade<<<occupancy_grid(c, k_photon_shade, 128), 128, 0, c->stream>>>(L, level);
             c->stats.kernel_launches++;
-            if (level > 1) {
-                k_photon_deposit<<<occupancy_grid(c, k_photon_deposit, 128), 128, 0, c->stream>>>(L, level);
-                c->stats.kernel_launches++;
-            }
         }
+        // deposit requests of all bounce levels in one launch (deposits do not feed back into the photon paths)
+        k_photon_deposit<<<occupancy_grid(c, k_photon_deposit, 128), 128, 0, c->stream>>>(L, 0);
+        c->stats.kernel_launches++;
         k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap, 0);
         c->stats.kernel_launches++;
     }

@@ -29,7 +29,7 @@ struct WhittedLaunch {
     float4 *so, *sd, *sc_contrib;     // shadow queue: {o,-} {d, slot} {contribution,-}
     float4* accum;             // per slot: radiance
     float2* filmpos;           // per slot: p_film (x < -1e29: inactive slot)
-    int* counters;             // [level] rays in queue at that level (1-based), [32 + level] shadow rays emitted at level
+    int* counters;             // [level] rays in queue at that level (1-based), [32] shadow rays of the whole batch
     int cap_rays, cap_shadow;
     float4* film_rgbw;         // per film pixel: sum(L*w) rgb, sum(w)
 };
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
             if (is_black3(f)) continue;
             const float3 contrib = w * ((f * Li) * fabsf(dot3(wi, it.ns)) / 1.0f);
             const float3 sdir = lpos - it.p;                 // spawn_ray(p0, p1): un-normalised, t_max = Inf (Q5)
-            const int q = queue_claim(&L.counters[32 + level]);
+            const int q = queue_claim(&L.counters[32]);
             if (q < L.cap_shadow) {
                 L.so[q] = f4(it.p + 1e-6f * sdir, TR_INF);
                 L.sd[q] = f4(sdir, d4.w);
@@ -174,7 +174,8 @@ __global__ void k_wh_batch_stats(int* counters, unsigned long long* stats, int m
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (batch_flag) *batch_flag = counters[IC_OVERFLOW];
         unsigned long long e = 0, s = 0;
-        for (int l = 1; l <= max_depth; ++l) { e += min(counters[l], cap_rays); s += min(counters[32 + l], cap_shadow); }
+        for (int l = 1; l <= max_depth; ++l) e += min(counters[l], cap_rays);
+        s = min(counters[32], cap_shadow);
         if (!counters[IC_OVERFLOW]) { atomicAdd(&stats[ST_RAYS_EXTEND], e); atomicAdd(&stats[ST_RAYS_SHADOW], s); }
     }
 }
@@ -201,9 +202,11 @@ static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long 
                       L.hits, st + ST_NODES, ic + IC_ERROR);
         k_wh_shade<<<occupancy_grid(c, k_wh_shade, 128), 128, 0, c->cur_stream>>>(L, level);
         c->stats.kernel_launches++;
-        launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
-                      (const int*)(ic + 32 + level), L.cap_shadow, L.accum, st + ST_NODES, ic + IC_ERROR);
     }
+    // one any-hit launch over the shadow rays of ALL bounce levels of the batch (they only feed the accumulators): a
+    // single wide launch instead of max_depth launches that each wait for their slowest ray
+    launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
+                  (const int*)(ic + 32), L.cap_shadow, L.accum, st + ST_NODES, ic + IC_ERROR);
     k_wh_splat<<<g_stream, 256, 0, c->cur_stream>>>(L);
     k_wh_batch_stats<<<1, 32, 0, c->cur_stream>>>(ic, st, L.max_depth, L.cap_rays, L.cap_shadow, batch_flag);
     c->stats.kernel_launches += 2;
@@ -255,7 +258,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     nb = (total_slots + batch - 1) / batch;
     const size_t cap_rays = (size_t)batch * (size_t)c->cap_percent / 100;
     const int shadow_mult = std::max(1, std::min(L.sc.n_lights, 4));
-    const size_t cap_shadow = cap_rays * shadow_mult;
+    const size_t cap_shadow = cap_rays * shadow_mult * 2;     // all bounce levels of a batch share one shadow queue
     L.cap_rays = (int)cap_rays; L.cap_shadow = (int)cap_shadow;
     for (int k = 0; k < 7; ++k) TR_CUDA(c, c->b_queue[k].ensure(K * cap_rays * sizeof(float4)));
     for (int k = 7; k < 10; ++k) TR_CUDA(c, c->b_queue[k].ensure(K * cap_shadow * sizeof(float4)));
