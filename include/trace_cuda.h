@@ -79,7 +79,8 @@ typedef struct trace_material {
 } trace_material;
 
 /* ---- lights (src/lights/point.jl, spot.jl) ---- */
-enum { TRACE_LIGHT_POINT = 0, TRACE_LIGHT_SPOT = 1 };
+enum { TRACE_LIGHT_POINT = 0, TRACE_LIGHT_SPOT = 1,
+       TRACE_LIGHT_DIRECTIONAL = 2 /* src/lights/directional.jl: position = normalised world direction, cos_total_width = world_radius */ };
 typedef struct trace_light {
     uint32_t kind;
     float m[16];         /* light_to_world.m, row-major */

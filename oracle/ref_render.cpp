@@ -326,7 +326,10 @@ extern "C" int ref_render_sppm(const ref_scene* rs, const trace_camera* cam, con
     }
     const float gamma = 2.0f / 3.0f;
     std::vector<float> powers;
-    for (const auto& l : s.lights) powers.push_back(to_Y(light_power(l)));
+    for (const auto& l : s.lights) {
+        if (l.kind == TRACE_LIGHT_DIRECTIONAL) return 2;      // no sample_le for DirectionalLight in the reference
+        powers.push_back(to_Y(light_power(l)));
+    }
     if (powers.empty()) return 1;
     Distribution1D light_distr(powers);
     const int tile_size = 16;

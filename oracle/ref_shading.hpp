@@ -471,6 +471,13 @@ inline float spot_falloff(const trace_light& l, V3 w) {                         
     return pow4(d);
 }
 inline void sample_li(const trace_light& l, V3 p, RGB& radiance, V3& wi, float& pdf, V3& light_pos) {   // point.jl:50-58, spot.jl:22-30
+    if (l.kind == TRACE_LIGHT_DIRECTIONAL) {       // directional.jl:39-47: position = direction, cos_total_width = world_radius
+        wi = V3(l.position[0], l.position[1], l.position[2]);
+        pdf = 1.0f;
+        light_pos = p + wi * (2.0f * l.cos_total_width);
+        radiance = RGB(l.I[0], l.I[1], l.I[2]);
+        return;
+    }
     V3 pos(l.position[0], l.position[1], l.position[2]);
     wi = normalize(pos - p);
     pdf = 1.0f;
@@ -484,6 +491,7 @@ inline void sample_li(const trace_light& l, V3 p, RGB& radiance, V3& wi, float& 
 inline RGB light_power(const trace_light& l) {                                   // point.jl:74-76, spot.jl:42-44
     RGB I(l.I[0], l.I[1], l.I[2]);
     if (l.kind == TRACE_LIGHT_POINT) return (4.0f * PI_F) * I;
+    if (l.kind == TRACE_LIGHT_DIRECTIONAL) return (I * PI_F) * (l.cos_total_width * l.cos_total_width);   // directional.jl:54-56
     return ((I * 2.0f) * PI_F) * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width));
 }
 struct LeSample { RGB le; Ray ray; V3 n; float pdf_pos, pdf_dir; };

@@ -282,6 +282,22 @@ def test_whitted_tessellated_image(T, ctx):
     assert float(ref[..., 1].max()) > 0
 
 
+def test_whitted_thin_lens_camera(T, ctx):
+    """lens_radius > 0: the depth-of-field branch of generate_ray (perspective.jl:94-103) with lens samples from the
+    shared counter-based RNG (dimensions 2-3)."""
+    scene, _, _ = T.scenes.shadows(resolution=64)
+    film = T.Film([64, 64], T.Bounds2([0, 0], [1, 1]), T.LanczosSincFilter([1, 1], 3.0), 1.0, 1.0, None)
+    camera = T.PerspectiveCamera(T.look_at([0, 15, 50], [0, 0, -2], [0, 1, 0]), T.Bounds2([-1, -1], [1, 1]), 0.0, 1.0,
+                                 0.6, 54.0, 90.0, film)
+    gpu, ref, st, cnt = whitted_pair(T, ctx, scene, camera, 8, 4)
+    rel_mse, frac, werr = image_report(gpu, ref, "whitted/thin-lens")
+    assert werr < 1e-5 and rel_mse < 1e-6 and frac > 0.999 and float(ref[..., 1].max()) > 0
+    # and it really blurs: differs from the pinhole render
+    pin = T.PerspectiveCamera(T.look_at([0, 15, 50], [0, 0, -2], [0, 1, 0]), T.Bounds2([-1, -1], [1, 1]), 0.0, 1.0, 0.0, 54.0, 90.0, film)
+    gpu2, _, _, _ = whitted_pair(T, ctx, scene, pin, 8, 4)
+    assert np.abs(gpu2[..., :3] - gpu[..., :3]).max() > 1e-2 * np.abs(gpu2[..., :3]).max()
+
+
 def test_whitted_accumulates_into_film(T, ctx):
     """The reference never clears the film (merge_film_tile! adds, Q14): a second render doubles xyz and weights."""
     scene, camera, _ = T.scenes.shadows(resolution=48)
@@ -379,6 +395,56 @@ def test_sppm_caustic_glass_image(T, ctx):
     assert rel_mse < 2e-2 and frac > 0.85
     assert abs(st["rays_extend"] - int(cnt[0])) <= 1e-3 * int(cnt[0])
     assert float(ref.max()) > 0
+
+
+def _appearance_scene(T, res=72):
+    """Rough glass (microfacet reflection + transmission), Oren-Nayar matte, plastic, a DirectionalLight (preprocessed)
+    next to a point light: the appearance surface SURVEY.md §8f.3 lists."""
+    rough_glass = T.GlassMaterial(T.ConstantTexture(T.RGBSpectrum(1.0)), T.ConstantTexture(T.RGBSpectrum(0.9)),
+                                  T.ConstantTexture(0.2), T.ConstantTexture(0.35), T.ConstantTexture(1.5), True)
+    oren = T.MatteMaterial(T.ConstantTexture(T.RGBSpectrum(0.8, 0.6, 0.4)), T.ConstantTexture(35.0))
+    plastic = T.PlasticMaterial(T.ConstantTexture(T.RGBSpectrum(0.3, 0.5, 0.3)), T.ConstantTexture(T.RGBSpectrum(0.4)),
+                                T.ConstantTexture(0.15), True)
+    prims = [T.GeometricPrimitive(T.Sphere(T.ShapeCore(T.translate([0.3, 0.25, -2.4]), False), 0.25, 360.0), rough_glass),
+             T.GeometricPrimitive(T.Sphere(T.ShapeCore(T.translate([0.75, 0.2, -2.5]), False), 0.2, 360.0), plastic)]
+    tris = T.create_triangle_mesh(T.ShapeCore(T.translate([0, 0, -2]), False), 4, [1, 2, 3, 1, 4, 3, 2, 3, 5, 6, 5, 3], 6,
+                                  [[0, 0, 0], [0, 0, -1], [1, 0, -1], [1, 0, 0], [0, 1, -1], [1, 1, -1]],
+                                  [[0, 1, 0]] * 4 + [[0, 0, 1]] * 2)
+    prims += [T.GeometricPrimitive(t, oren) for t in tris]
+    scene = T.Scene([T.PointLight(T.translate([-1, 1, 0]), T.RGBSpectrum(10.0))], T.BVHAccel(prims, 1))
+    sun = T.DirectionalLight(T.rotate_x(20.0), T.RGBSpectrum(1.5, 1.4, 1.2), [0.3, 1.0, 0.6])
+    sun.preprocess(scene)
+    scene.lights.append(sun)
+    film = T.Film([res, res], T.Bounds2([0, 0], [1, 1]), T.LanczosSincFilter([1, 1], 3.0), 1.0, 1.0, None)
+    camera = T.PerspectiveCamera(T.look_at([0, 15, 50], [0, 0, -2], [0, 1, 0]), T.Bounds2([-1, -1], [1, 1]), 0, 1, 0, 1e6, 90.0, film)
+    return scene, camera
+
+
+def test_whitted_appearance_surface(T, ctx):
+    scene, camera = _appearance_scene(T)
+    gpu, ref, st, cnt = whitted_pair(T, ctx, scene, camera, 4, 5)
+    rel_mse, frac, werr = image_report(gpu, ref, "whitted/rough-glass+oren-nayar+directional")
+    assert float(ref[..., 1].max()) > 0
+    assert werr < 1e-5 and rel_mse < 1e-5 and frac > 0.995
+    assert st["rays_extend"] == int(cnt[0]) and st["rays_shadow"] == int(cnt[1])
+
+
+def test_sppm_appearance_surface(T, ctx):
+    """Same materials through the SPPM passes (sample_f of the microfacet lobes, Oren-Nayar visible points); the
+    directional light is dropped: the reference has no sample_le for it and both sides refuse it."""
+    scene, camera = _appearance_scene(T, 64)
+    with_sun = scene
+    scene = T.Scene(with_sun.lights[:1], with_sun.aggregate)
+    gpu, ref, st, cnt = sppm_pair(T, ctx, scene, camera, 0.04, 5, 3, 60000)
+    g4 = np.concatenate([gpu, np.ones_like(gpu[..., :1])], -1)
+    r4 = np.concatenate([ref, np.ones_like(ref[..., :1])], -1)
+    rel_mse, frac, _ = image_report(g4, r4, "sppm/rough-glass+oren-nayar")
+    print("sppm rays gpu", st["rays_extend"], st["rays_shadow"], "oracle", cnt, "deposits", st["sppm_deposits"])
+    assert rel_mse < 2e-2 and frac > 0.9 and float(ref.max()) > 0
+    ctx.upload(with_sun)
+    cam, fd = camera.pod(), camera.film.desc()
+    rc = ctx.lib.trace_sppm_begin(ctx.h, C.byref(cam), C.byref(fd), 0.04, 5, 1000, C.c_uint64(1))
+    assert rc != 0 and b"DirectionalLight" in ctx.lib.trace_last_error(ctx.h)
 
 
 def test_integrator_functors(T, ctx, tmp_path):

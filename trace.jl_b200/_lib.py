@@ -12,7 +12,7 @@ NODE_LEAF = 0xC0000000
 PRIM_TRIANGLE, PRIM_SPHERE = 0, 1
 TRI_FLIP, TRI_HAS_NORMALS = 1, 2
 MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_PLASTIC = 0, 1, 2, 3
-LIGHT_POINT, LIGHT_SPOT = 0, 1
+LIGHT_POINT, LIGHT_SPOT, LIGHT_DIRECTIONAL = 0, 1, 2
 
 node_dtype = np.dtype([("bmin", "<f4", 3), ("bmax", "<f4", 3), ("offset", "<u4"), ("meta", "<u4")])
 prim_dtype = np.dtype([("kind", "<u4"), ("index", "<u4"), ("material", "<u4"), ("original", "<u4")])

@@ -226,11 +226,16 @@ extern "C" int trace_scene_upload(trace_ctx* c, const trace_scene_desc* d) {
         for (int k = 0; k < 3; ++k) { dm.a[k] = m.a[k]; dm.b[k] = m.b[k]; }
         dm.eta = m.eta;
         if (m.kind == TRACE_MAT_MATTE) {
-            float sigma = m.rough_u > 90.0f ? 90.0f : (m.rough_u < 0.0f ? 0.0f : m.rough_u);
-            if (sigma != 0.0f) return c->fail("material %lld: Oren-Nayar (sigma > 0) is not on the GPU path yet (SURVEY.md §8f.3)", (long long)i);
+            // sigma = clamp(sigma, 0, 90); sigma == 0 -> Lambertian, else Oren-Nayar with A, B (microfacet.jl:12-18)
+            const float sigma = m.rough_u > 90.0f ? 90.0f : (m.rough_u < 0.0f ? 0.0f : m.rough_u);
+            dm.specular = sigma == 0.0f ? 1u : 0u;
+            const float sr = sigma * (3.1415927f / 180.0f), s2 = sr * sr;
+            dm.alpha_u = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));
+            dm.alpha_v = 0.45f * s2 / (s2 + 0.09f);
         } else if (m.kind == TRACE_MAT_GLASS) {
             dm.specular = (m.rough_u == 0.0f && m.rough_v == 0.0f) ? 1u : 0u;
-            if (!dm.specular) return c->fail("material %lld: rough glass (microfacet transmission) is not on the GPU path yet (SURVEY.md §8f.3)", (long long)i);
+            const float ru = m.remap ? remap_alpha(m.rough_u) : m.rough_u, rv = m.remap ? remap_alpha(m.rough_v) : m.rough_v;
+            dm.alpha_u = fmaxf(1e-3f, ru); dm.alpha_v = fmaxf(1e-3f, rv);      // material.jl:93-98, microfacet.jl:58-62
         } else if (m.kind == TRACE_MAT_PLASTIC) {
             float r = m.remap ? remap_alpha(m.rough_u) : m.rough_u;
             dm.alpha_u = dm.alpha_v = fmaxf(1e-3f, r);           // TrowbridgeReitzDistribution clamps, microfacet.jl:58-62
@@ -245,7 +250,8 @@ extern "C" int trace_scene_upload(trace_ctx* c, const trace_scene_desc* d) {
         memcpy(dl.m, l.m, sizeof(dl.m)); memcpy(dl.inv_m, l.inv_m, sizeof(dl.inv_m));
         for (int k = 0; k < 3; ++k) { dl.I[k] = l.I[k]; dl.pos[k] = l.position[k]; }
         dl.cos_total = l.cos_total_width; dl.cos_falloff = l.cos_falloff_start;
-        if (l.kind != TRACE_LIGHT_POINT && l.kind != TRACE_LIGHT_SPOT) return c->fail("light %lld: unknown kind", (long long)i);
+        if (l.kind != TRACE_LIGHT_POINT && l.kind != TRACE_LIGHT_SPOT && l.kind != TRACE_LIGHT_DIRECTIONAL)
+            return c->fail("light %lld: unknown kind", (long long)i);
         lights[i] = dl;
     }
     // --- upload

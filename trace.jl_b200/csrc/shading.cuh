@@ -8,7 +8,8 @@
 #include "traverse.cuh"
 
 enum : uint32_t { LB_REFLECTION = 1, LB_TRANSMISSION = 2, LB_DIFFUSE = 4, LB_GLOSSY = 8, LB_SPECULAR = 16, LB_ALL = 31 };
-enum : int { LK_LAMBERT = 0, LK_SPEC_REFL = 1, LK_SPEC_TRANS = 2, LK_FRESNEL_SPEC = 3, LK_MICRO_REFL = 4 };
+enum : int { LK_LAMBERT = 0, LK_SPEC_REFL = 1, LK_SPEC_TRANS = 2, LK_FRESNEL_SPEC = 3, LK_MICRO_REFL = 4, LK_MICRO_TRANS = 5,
+             LK_OREN_NAYAR = 6 };
 
 struct Interaction {
     float3 p, wo, ng, ns, dpdu;     // core.p, core.wo, core.n, shading.n, shading.∂p∂u
@@ -24,7 +25,7 @@ struct Lobe {
     float eta_a, eta_b;
     int fresnel;            // 0 FresnelNoOp, 1 FresnelDielectric(fi, ft)
     float fi, ft;
-    float ax, ay;
+    float ax, ay;           // Trowbridge-Reitz alphas; Oren-Nayar: A and B (microfacet.jl:12-18)
 };
 struct LobeSet { Lobe l[2]; int n; };
 
@@ -123,24 +124,29 @@ __device__ __forceinline__ void material_lobes(const DeviceMaterial& m, bool mul
     const float3 A = clamp_spectrum(m.a), B = clamp_spectrum(m.b);
     if (m.kind == TRACE_MAT_MATTE) {
         if (is_black3(A)) return;
-        Lobe l = make_lobe(LK_LAMBERT, LB_DIFFUSE | LB_REFLECTION); l.r = A; s.l[s.n++] = l;
+        if (m.specular) {                // sigma == 0 -> Lambertian (material.jl:26-30)
+            Lobe l = make_lobe(LK_LAMBERT, LB_DIFFUSE | LB_REFLECTION); l.r = A; s.l[s.n++] = l;
+        } else {
+            Lobe l = make_lobe(LK_OREN_NAYAR, LB_DIFFUSE | LB_REFLECTION); l.r = A; l.ax = m.alpha_u; l.ay = m.alpha_v; s.l[s.n++] = l;
+        }
     } else if (m.kind == TRACE_MAT_MIRROR) {
         if (is_black3(A)) return;
         Lobe l = make_lobe(LK_SPEC_REFL, LB_SPECULAR | LB_REFLECTION); l.r = A; s.l[s.n++] = l;
     } else if (m.kind == TRACE_MAT_GLASS) {
         if (is_black3(A) && is_black3(B)) return;
-        if (multi) {
+        const bool spec = m.specular != 0u;
+        if (spec && multi) {
             Lobe l = make_lobe(LK_FRESNEL_SPEC, LB_SPECULAR | LB_TRANSMISSION | LB_REFLECTION);
             l.r = A; l.t = B; l.eta_a = 1.0f; l.eta_b = m.eta; s.l[s.n++] = l;
             return;
         }
         if (!is_black3(A)) {
-            Lobe l = make_lobe(LK_SPEC_REFL, LB_SPECULAR | LB_REFLECTION);
-            l.r = A; l.fresnel = 1; l.fi = 1.0f; l.ft = m.eta; s.l[s.n++] = l;
+            Lobe l = spec ? make_lobe(LK_SPEC_REFL, LB_SPECULAR | LB_REFLECTION) : make_lobe(LK_MICRO_REFL, LB_REFLECTION | LB_GLOSSY);
+            l.r = A; l.fresnel = 1; l.fi = 1.0f; l.ft = m.eta; l.ax = m.alpha_u; l.ay = m.alpha_v; s.l[s.n++] = l;
         }
         if (!is_black3(B)) {
-            Lobe l = make_lobe(LK_SPEC_TRANS, LB_SPECULAR | LB_TRANSMISSION);
-            l.t = B; l.eta_a = 1.0f; l.eta_b = m.eta; s.l[s.n++] = l;
+            Lobe l = spec ? make_lobe(LK_SPEC_TRANS, LB_SPECULAR | LB_TRANSMISSION) : make_lobe(LK_MICRO_TRANS, LB_TRANSMISSION | LB_GLOSSY);
+            l.t = B; l.eta_a = 1.0f; l.eta_b = m.eta; l.ax = m.alpha_u; l.ay = m.alpha_v; s.l[s.n++] = l;
         }
     } else {   // TRACE_MAT_PLASTIC
         if (!is_black3(A)) { Lobe l = make_lobe(LK_LAMBERT, LB_DIFFUSE | LB_REFLECTION); l.r = A; s.l[s.n++] = l; }
@@ -282,6 +288,30 @@ __device__ __forceinline__ float3 lobe_f(const Lobe& l, float3 wo, float3 wi) {
         float G = 1.0f / (1.0f + tr_lambda(l, wo) + tr_lambda(l, wi));
         return l.r * tr_D(l, wh) * G * fr / (4.0f * ci * co);
     }
+    if (l.kind == LK_MICRO_TRANS) {                    // microfacet.jl:280-305
+        if (same_hemi(wo, wi)) return f3s(0.0f);
+        const float co = wo.z, ci = wi.z;
+        if (co == 0.0f || ci == 0.0f) return f3s(0.0f);
+        const float eta = wo.z > 0.0f ? (l.eta_b / l.eta_a) : (l.eta_a / l.eta_b);
+        float3 wh = normalize3(wo + wi * eta);
+        if (wh.z < 0.0f) wh = -wh;
+        const float d_o = dot3(wo, wh), d_i = dot3(wi, wh);
+        if (d_o * d_i > 0.0f) return f3s(0.0f);
+        const float fr = fresnel_dielectric(d_o, l.eta_a, l.eta_b);
+        const float denom = d_o + eta * d_i;
+        const float dd = tr_D(l, wh), dg = 1.0f / (1.0f + tr_lambda(l, wo) + tr_lambda(l, wi));
+        const float v = fabsf(dd * dg * d_o * d_i * (eta * eta) * (1.0f * 1.0f) / (ci * co * (denom * denom)));   // factor = 1 (Q6)
+        return ((f3s(1.0f) - f3s(fr)) * l.t) * v;
+    }
+    if (l.kind == LK_OREN_NAYAR) {                     // microfacet.jl:21-42
+        const float si = sin_th(wi), so = sin_th(wo);
+        float max_cos = 0.0f;
+        if (si > 1e-4f && so > 1e-4f) max_cos = fmaxf(0.0f, cos_ph(wi) * cos_ph(wo) + sin_ph(wi) * sin_ph(wo));
+        float sa, tb;
+        if (wi.z > fabsf(wo.z)) { sa = so; tb = si / fabsf(wi.z); }        // abs(Bool) quirk, Q18
+        else { sa = si; tb = so / fabsf(wo.z); }
+        return l.r * (1.0f / TR_PI) * (l.ax + l.ay * max_cos * sa * tb);
+    }
     return f3s(0.0f);      // delta lobes
 }
 __device__ __forceinline__ float lobe_pdf(const Lobe& l, float3 wo, float3 wi) {
@@ -290,6 +320,15 @@ __device__ __forceinline__ float lobe_pdf(const Lobe& l, float3 wo, float3 wi) {
         if (!same_hemi(wo, wi)) return 0.0f;
         float3 wh = normalize3(wo + wi);
         return tr_pdf(l, wo, wh) / dot3(4.0f * wo, wh);
+    }
+    if (l.kind == LK_MICRO_TRANS) {                    // microfacet.jl:322-337
+        if (same_hemi(wo, wi)) return 0.0f;
+        const float eta = wo.z > 0.0f ? (l.eta_b / l.eta_a) : (l.eta_a / l.eta_b);
+        const float3 wh = normalize3(wo + wi * eta);
+        const float d_o = dot3(wo, wh), d_i = dot3(wi, wh);
+        if (d_o * d_i > 0.0f) return 0.0f;
+        const float denom = d_o + eta * d_i;
+        return tr_pdf(l, wo, wh) * fabsf(d_i * (eta * eta) / (denom * denom));
     }
     return same_hemi(wo, wi) ? fabsf(wi.z) * (1.0f / TR_PI) : 0.0f;
 }
@@ -330,6 +369,14 @@ __device__ __forceinline__ LobeSample lobe_sample(const Lobe& l, float3 wo, floa
         s.wi = wi;
         s.pdf = lobe_pdf(l, wo, wh);          // Q27: BxDF-level pdf evaluated with wh in the wi slot
         s.f = lobe_f(l, wo, wi);
+    } else if (l.kind == LK_MICRO_TRANS) {             // microfacet.jl:307-320
+        if (wo.z == 0.0f) return s;
+        float3 wh = tr_sample_wh(l, wo, u0, u1);
+        if (dot3(wo, wh) < 0.0f) return s;
+        const float eta = wo.z > 0.0f ? (l.eta_b / l.eta_a) : (l.eta_a / l.eta_b);
+        float3 wi;
+        if (!refract(wo, wh, eta, wi)) return s;
+        s.wi = wi; s.pdf = lobe_pdf(l, wo, wi); s.f = lobe_f(l, wo, wi);
     } else {
         float3 wi = cosine_hemisphere(u0, u1);
         if (wo.z < 0.0f) wi = f3(wi.x, wi.y, -wi.z);
@@ -415,9 +462,18 @@ __device__ __forceinline__ float3 sample_li(const DeviceLight& l, float3 p, floa
     if (l.kind == TRACE_LIGHT_POINT) return I / d2;
     return (I * spot_falloff(l, -wi)) / d2;
 }
+// DirectionalLight.sample_li (lights/directional.jl:39-47): wi = direction, Li = I, the shadow ray ends at
+// p + direction * 2 * world_radius (world_radius stays 0 unless the user ran preprocess!)
+__device__ __forceinline__ float3 sample_li_any(const DeviceLight& l, float3 p, float3& wi, float3& lpos) {
+    if (l.kind != TRACE_LIGHT_DIRECTIONAL) return sample_li(l, p, wi, lpos);
+    wi = f3(l.pos[0], l.pos[1], l.pos[2]);
+    lpos = p + wi * (2.0f * l.cos_total);
+    return f3(l.I[0], l.I[1], l.I[2]);
+}
 __device__ __forceinline__ float3 light_power(const DeviceLight& l) {
     float3 I = f3(l.I[0], l.I[1], l.I[2]);
     if (l.kind == TRACE_LIGHT_POINT) return (4.0f * TR_PI) * I;
+    if (l.kind == TRACE_LIGHT_DIRECTIONAL) return (I * TR_PI) * (l.cos_total * l.cos_total);
     return ((I * 2.0f) * TR_PI) * (1.0f - 0.5f * (l.cos_falloff + l.cos_total));
 }
 

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level)
             const int ln = max(1, min((int)ceilf(ul * (float)nl), nl));
             const float light_pdf = 1.0f / (float)nl;
             float3 wi, lpos;
-            const float3 Li = sample_li(L.sc.lights[ln - 1], it.p, wi, lpos);
+            const float3 Li = sample_li_any(L.sc.lights[ln - 1], it.p, wi, lpos);
             if (!is_black3(Li)) {
                 const float3 f = bsdf_f(lobes, fr, it.wo, wi, LB_ALL & ~LB_SPECULAR) * fabsf(dot3(wi, it.ns));
                 if (!is_black3(f)) {
@@ -548,7 +548,11 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     TR_CUDA(c, cudaMemcpyAsync(hl.data(), c->scene.lights, (size_t)nl * sizeof(DeviceLight), cudaMemcpyDeviceToHost, c->stream));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
     std::vector<float> func((size_t)nl), cdf((size_t)nl + 1);
-    for (int i = 0; i < nl; ++i) func[i] = host_luminance_power(c, hl[i]);
+    for (int i = 0; i < nl; ++i) {
+        // the reference defines no sample_le for DirectionalLight (lights/directional.jl): its photon pass would throw
+        if (hl[i].kind == TRACE_LIGHT_DIRECTIONAL) { sppm_free(c); return c->fail("SPPM: DirectionalLight cannot emit photons (no sample_le in the reference)"); }
+        func[i] = host_luminance_power(c, hl[i]);
+    }
     cdf[0] = 0.0f;
     for (int i = 1; i <= nl; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / (float)nl;
     const float func_int = cdf[nl];

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
         // direct lighting: one shadow ray per light (sampler.jl:83-92)
         for (int li = 0; li < L.sc.n_lights; ++li) {
             float3 wi, lpos;
-            const float3 Li = sample_li(L.sc.lights[li], it.p, wi, lpos);
+            const float3 Li = sample_li_any(L.sc.lights[li], it.p, wi, lpos);
             if (is_black3(Li)) continue;
             const float3 f = bsdf_f(lobes, fr, it.wo, wi, LB_ALL);
             if (is_black3(f)) continue;

@@ -363,6 +363,33 @@ class SpotLight:
                 self.cos_total_width, self.cos_falloff_start)
 
 
+class DirectionalLight:
+    """src/lights/directional.jl:1-56.  world_radius / world_center stay 0 until preprocess!(light, scene) is called,
+    exactly like the reference (Scene's constructor does not do it, src/Trace.jl:184)."""
+
+    def __init__(self, light_to_world, l, direction):
+        from .geometry import normalize
+        self.light_to_world = light_to_world
+        self.world_to_light = light_to_world.inv()
+        self.i = l
+        self.direction = normalize(light_to_world.vector(direction))
+        self.world_radius = f32(0)
+        self.world_center = _v3(0.0)
+
+    def preprocess(self, scene):                      # preprocess!, directional.jl:35-37 + bounding_sphere, bounds.jl:145-149
+        b = scene.bound
+        center = ((b.p_min + b.p_max) / f32(2)).astype(np.float32)
+        inside = bool(np.all(center >= b.p_min) and np.all(center <= b.p_max))
+        d = center - b.p_max
+        self.world_center = center
+        self.world_radius = f32(np.sqrt(f32(f32(f32(d[0] * d[0]) + f32(d[1] * d[1])) + f32(d[2] * d[2])))) if inside else f32(0)
+        scene._flat = None
+
+    def pod(self):
+        return (_lib.LIGHT_DIRECTIONAL, self.light_to_world.m, self.light_to_world.inv_m, self.i.c, self.direction,
+                self.world_radius, 0.0)
+
+
 class Scene:
     """Scene(lights, aggregate), src/Trace.jl:176-187."""
 
