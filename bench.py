@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (scene kwargs, spp, depth)
     "tess-1M": (dict(cells=600, stacks=266, slices=264, res=(1920, 1080), window=((-50.0, -28.125), (50.0, 28.125))), 16, 5),
+    # BASELINE.json configs[4] (C5): 10 002 224 triangles, 4096^2 x 64 spp, depth 8 - meant for 8 GPUs
+    "tess-10M": (dict(cells=1900, stacks=835, slices=834, res=(4096, 4096), window=((-50.0, -50.0), (50.0, 50.0))), 64, 8),
     "tess-small": (dict(cells=64, stacks=34, slices=32, res=(480, 270), window=((-50.0, -28.125), (50.0, 28.125))), 4, 5),
 }
 METRIC = "Mrays/sec (closest-hit + shadow)"

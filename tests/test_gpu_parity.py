@@ -287,8 +287,10 @@ def test_whitted_thin_lens_camera(T, ctx):
     shared counter-based RNG (dimensions 2-3)."""
     scene, _, _ = T.scenes.shadows(resolution=64)
     film = T.Film([64, 64], T.Bounds2([0, 0], [1, 1]), T.LanczosSincFilter([1, 1], 3.0), 1.0, 1.0, None)
+    # the reference's camera looks down -z (look_at: z_axis = normalize(position - target)), so ray.d[3] < 0 and the
+    # plane of focus t = focal_distance / ray.d[3] lies in front of the camera only for a NEGATIVE focal_distance
     camera = T.PerspectiveCamera(T.look_at([0, 15, 50], [0, 0, -2], [0, 1, 0]), T.Bounds2([-1, -1], [1, 1]), 0.0, 1.0,
-                                 0.6, 54.0, 90.0, film)
+                                 0.6, -54.0, 90.0, film)
     gpu, ref, st, cnt = whitted_pair(T, ctx, scene, camera, 8, 4)
     rel_mse, frac, werr = image_report(gpu, ref, "whitted/thin-lens")
     assert werr < 1e-5 and rel_mse < 1e-6 and frac > 0.999 and float(ref[..., 1].max()) > 0
@@ -312,7 +314,7 @@ def test_whitted_accumulates_into_film(T, ctx):
 
 def test_whitted_queue_overflow_retry(T, ctx):
     """Glass spawns a reflected and a transmitted ray per hit (sampler.jl:95-98), so a bounce level can hold more rays
-    than the batch has samples.  With the queue capacity squeezed to 110 % of the batch the queues overflow: the batch
+    than the batch has samples.  With the queue capacity squeezed to 100 % of the batch the queues overflow: the batch
     is not splatted and is re-run in halves - same image as the roomy run, and the oracle agrees."""
     glass = T.GlassMaterial(T.ConstantTexture(T.RGBSpectrum(1.0)), T.ConstantTexture(T.RGBSpectrum(1.0)), T.ConstantTexture(0.0),
                             T.ConstantTexture(0.0), T.ConstantTexture(1.5), True)
@@ -332,7 +334,7 @@ def test_whitted_queue_overflow_retry(T, ctx):
     ctx.check(ctx.lib.trace_render_whitted(ctx.h, C.byref(cam), C.byref(fd), 4, 8, C.c_uint64(5), T._lib.ptr(a)))
     n_over = ctx.stats()["queue_overflows"]
     b = np.zeros_like(a)
-    ctx.set_option("cap_percent", 110)
+    ctx.set_option("cap_percent", 100)      # 25 600 slots per batch < 25 830 rays at bounce level 2
     ctx.set_option("batch", 8192)
     ctx.reset_stats()
     ctx.check(ctx.lib.trace_render_whitted(ctx.h, C.byref(cam), C.byref(fd), 4, 8, C.c_uint64(5), T._lib.ptr(b)))

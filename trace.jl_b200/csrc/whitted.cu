@@ -250,9 +250,12 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     // batches of (at most) c->batch samples, evened out.  Deep bounce levels hold few but expensive rays (a launch
     // cannot end before its slowest ray: ~0.2 ms for a 1000-node walk), so batches are large and up to `lanes` of them
     // run concurrently on side streams, each lane with its own queues and counters.
-    long long nb = std::max<long long>(1, (total_slots + c->batch - 1) / c->batch);
+    // c->batch bounds the samples in flight over ALL lanes (queue memory ~ 350 B per sample in flight)
     int K = 1;
-    if (total_slots >= (long long)c->lanes * 131072) { K = c->lanes; nb = std::max<long long>(nb, K); }
+    if (total_slots >= (long long)c->lanes * 131072) K = c->lanes;
+    const long long per_lane = std::max<long long>(65536, c->batch / K);
+    long long nb = std::max<long long>(K, (total_slots + per_lane - 1) / per_lane);
+    nb = (nb + K - 1) / K * K;                                  // whole rounds of K lanes
     long long batch = (total_slots + nb - 1) / nb;
     batch = std::max<long long>(256, (batch + 255) / 256 * 256);
     nb = (total_slots + batch - 1) / batch;
