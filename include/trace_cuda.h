@@ -187,13 +187,19 @@ int trace_render_sppm(trace_ctx* ctx, const trace_camera* cam, const trace_film_
                       float initial_radius, int max_depth, int n_iterations, int64_t photons_per_iteration,
                       int write_frequency, uint64_t seed, trace_sppm_cb on_image, void* user,
                       float* rgb_out /* [crop_h][crop_w][3], image after the last iteration (sppm.jl:461-472) */);
-/* stepwise form used for multi-GPU photon sharding: begin; per iteration {camera_pass; photon_pass(range);
- * allreduce the buffer returned by trace_sppm_flux_device; update}; image; end. */
+/* stepwise form used for multi-GPU sharding (options "rank"/"world" set BEFORE trace_sppm_begin): begin; per iteration
+ * { camera_pass (this rank's image rows; with world == 1 it also builds the grid);
+ *   [world > 1: all-gather buffers 2..6, then trace_sppm_build_grid];
+ *   photon_pass(this rank's photon range); [world > 1: all-reduce(sum) buffer 0]; update };
+ * [world > 1: all-gather buffer 1]; image; end.  Per-pixel buffers are in storage order: image rows dealt round-robin
+ * to the ranks, each rank's rows contiguous (padded to ceil(H / world) rows), so rank r owns slice r of world. */
 int   trace_sppm_begin(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film,
                        float initial_radius, int max_depth, int64_t photons_per_iteration, uint64_t seed);
 int   trace_sppm_camera_pass(trace_ctx* ctx, int iteration);
 int   trace_sppm_photon_pass(trace_ctx* ctx, int iteration, int64_t photon_begin, int64_t photon_end);
-void* trace_sppm_flux_device(trace_ctx* ctx, int64_t* n_floats /* 4 per pixel: Phi.rgb, M */);
+int   trace_sppm_build_grid(trace_ctx* ctx);
+void* trace_sppm_flux_device(trace_ctx* ctx, int64_t* n_floats /* 4 per pixel slot: Phi.rgb, M */);
+void* trace_sppm_buffer_device(trace_ctx* ctx, int which /* 0 flux, 1 Ld, 2..6 visible points */, int64_t* n_floats);
 int   trace_sppm_update(trace_ctx* ctx);
 int   trace_sppm_image(trace_ctx* ctx, int iteration, float* rgb_out);
 int   trace_sppm_end(trace_ctx* ctx);

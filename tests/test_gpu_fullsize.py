@@ -107,3 +107,76 @@ def test_shadows_1024_sppm_properties(T, ctx):
     img_sharded = sess.image()
     sess.close()
     assert np.allclose(img_sharded, img1, rtol=2e-4, atol=1e-6)
+
+
+def test_sppm_row_sharding_protocol_on_one_gpu(T):
+    """The multi-GPU SPPM protocol (rows of the camera pass dealt round-robin, all-gather of the visible points,
+    photon ranges, all-reduce of the flux, all-gather of Ld) emulated with TWO contexts on one GPU: the exchanged
+    slices are copied between the contexts' buffers by hand.  The image must equal the unsharded render."""
+    import torch
+    from trace_jl_b200 import distributed as D
+    scene, camera, kw = T.scenes.shadows(resolution=151)        # 151 rows over 3 ranks: padding rows in play
+    iters, r0, depth = 3, 0.03, 5
+    ref_ctx = T.Context(0)
+    sess = D.SPPMSession(ref_ctx, scene, camera, r0, depth)
+    for _ in range(iters):
+        sess.step()
+    want = sess.image()
+    sess.close()
+    ref_ctx.close()
+
+    world = 3
+    ctxs = [T.Context(0) for _ in range(world)]
+    # no process group: we play the collectives ourselves
+    sessions = []
+    for r, c in enumerate(ctxs):
+        c.set_option("world", world)
+        c.set_option("rank", r)
+        cam, fd = camera.pod(), camera.film.desc()
+        c.upload(scene)
+        c.check(c.lib.trace_sppm_begin(c.h, C.byref(cam), C.byref(fd), r0, depth, -1, C.c_uint64(0x5EED0001)))
+        bufs = []
+        for which in range(7):
+            n = C.c_int64()
+            ptr = c.lib.trace_sppm_buffer_device(c.h, which, C.byref(n))
+            bufs.append(torch.as_tensor(D._DevicePtr(ptr, n.value), device="cuda:0"))
+        sessions.append(bufs)
+    photons = int(camera.film.crop_bounds.area())
+
+    def gather(which):
+        n = sessions[0][which].numel() // world
+        for dst in range(world):
+            for src in range(world):
+                if src != dst:
+                    for c in ctxs:
+                        c.synchronize()
+                    sessions[dst][which][src * n:(src + 1) * n].copy_(sessions[src][which][src * n:(src + 1) * n])
+        torch.cuda.synchronize()
+
+    for it in range(1, iters + 1):
+        for c in ctxs:
+            c.check(c.lib.trace_sppm_camera_pass(c.h, it))
+        for which in range(2, 7):
+            gather(which)
+        for c in ctxs:
+            c.check(c.lib.trace_sppm_build_grid(c.h))
+        for r, c in enumerate(ctxs):
+            b, e = D.photon_range(photons, r, world)
+            c.check(c.lib.trace_sppm_photon_pass(c.h, it, b, e))
+        for c in ctxs:
+            c.synchronize()
+        total = sum(bufs[0] for bufs in sessions)
+        torch.cuda.synchronize()
+        for bufs in sessions:
+            bufs[0].copy_(total)
+        torch.cuda.synchronize()
+        for c in ctxs:
+            c.check(c.lib.trace_sppm_update(c.h))
+    gather(1)
+    got = np.zeros_like(want)
+    ctxs[1].check(ctxs[1].lib.trace_sppm_image(ctxs[1].h, iters, T._lib.ptr(got)))
+    for c in ctxs:
+        c.check(c.lib.trace_sppm_end(c.h))
+        c.close()
+    assert np.isfinite(got).all() and float(want.max()) > 0
+    assert np.allclose(got, want, rtol=3e-4, atol=1e-6), float(np.abs(got - want).max())

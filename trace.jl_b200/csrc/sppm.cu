@@ -27,7 +27,11 @@ struct SppmLaunch {
     DeviceFilm film;
     int max_depth, iteration;
     uint64_t seed;
-    int W, H, npix;
+    int W, H, npix;            // npix = W*H is also the hash-table size (sppm.jl:141)
+    // pixel STORAGE order (all per-pixel arrays): image rows are dealt round-robin to `world` ranks and each rank's rows
+    // are contiguous, padded to chunk_rows rows - so a rank's visible points are one slice that an all-gather can move.
+    // world == 1: storage index == raster index.
+    int world, rank, chunk_rows, nstore;
     long long photons_per_iteration;
     // per-pixel state
     float4* Ld;        // rgb
@@ -55,20 +59,37 @@ struct SppmLaunch {
     unsigned long long* stats;
 };
 
+__device__ __forceinline__ bool storage_to_raster(const SppmLaunch& L, int s, int& x, int& y) {
+    const int row = s / L.W;
+    x = s - row * L.W;
+    const int owner = row / L.chunk_rows, local = row - owner * L.chunk_rows;
+    y = local * L.world + owner;
+    return y < L.H;                       // false: padding slot
+}
+__device__ __forceinline__ int raster_to_storage(const SppmLaunch& L, int x, int y) {
+    return ((y % L.world) * L.chunk_rows + y / L.world) * L.W + x;
+}
+
 // ---------------------------------------------------------------- camera pass
+// One camera path per pixel of THIS rank's rows (sppm.jl:184-196). The RNG is keyed by the raster pixel index, so the
+// visible points do not depend on the number of ranks.
 __global__ void __launch_bounds__(256) k_sppm_cam_generate(SppmLaunch L) {
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
-        const int px = L.film.crop_x0 + pix % L.W, py = L.film.crop_y0 + pix / L.W;
+    const int s0 = L.rank * L.chunk_rows * L.W, s1 = s0 + L.chunk_rows * L.W;
+    for (int st = s0 + blockIdx.x * blockDim.x + threadIdx.x; st < s1; st += gridDim.x * blockDim.x) {
+        int x, y;
+        if (!storage_to_raster(L, st, x, y)) continue;
+        const int pix = y * L.W + x;      // raster index: RNG key
+        const int px = L.film.crop_x0 + x, py = L.film.crop_y0 + y;
         const uint32_t it = (uint32_t)L.iteration;
         const float u0 = rng_uniform(L.seed, (uint32_t)pix, it, 0), u1 = rng_uniform(L.seed, (uint32_t)pix, it, 1);
         float l0 = 0.0f, l1 = 0.0f;
         if (L.cam.lens_radius > 0.0f) { l0 = rng_uniform(L.seed, (uint32_t)pix, it, 2); l1 = rng_uniform(L.seed, (uint32_t)pix, it, 3); }
         float3 o, d;
         generate_camera_ray(L.cam, (float)px + u0, (float)py + u1, l0, l1, o, d);
-        L.ro[0][pix] = f4(o, TR_INF);
-        L.rd[0][pix] = f4(d, __int_as_float(pix));
-        L.rw[0][pix] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-        if (pix == 0) L.counters[1] = L.npix;
+        const int q = queue_claim(&L.counters[1]);
+        L.ro[0][q] = f4(o, TR_INF);
+        L.rd[0][q] = f4(d, __int_as_float(st));          // the path carries its STORAGE slot
+        L.rw[0][q] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(pix));   // ... and its raster index (RNG key)
     }
 }
 
@@ -79,13 +100,14 @@ __global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level)
         const float4 h = L.hits[i];
         const uint32_t prim1 = __float_as_uint(h.y);
         if (prim1 == 0u) continue;
-        const float4 o4 = L.ro[cur][i], d4 = L.rd[cur][i];
-        float3 beta = xyz(L.rw[cur][i]);
+        const float4 o4 = L.ro[cur][i], d4 = L.rd[cur][i], w4 = L.rw[cur][i];
+        float3 beta = xyz(w4);
         float3 d = xyz(d4);
         if (d.x == 0.0f) d.x = 0.0f;
         if (d.y == 0.0f) d.y = 0.0f;
         if (d.z == 0.0f) d.z = 0.0f;
-        const int pix = __float_as_int(d4.w);
+        const int slot = __float_as_int(d4.w);      // storage slot of the pixel
+        const int pix = __float_as_int(w4.w);       // raster index: RNG key
         const uint32_t prim = prim1 - 1u;
         const float b2 = third_barycentric(L.sc, prim, xyz(o4), d);
         const Interaction it = build_interaction(L.sc, prim, xyz(o4), d, h.z, h.w, b2);
@@ -110,7 +132,7 @@ __global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level)
                     const int q = queue_claim(&L.counters[32]);
                     if (q >= L.cap_shadow) { L.counters[IC_OVERFLOW] = 1; continue; }
                     L.so[q] = f4(it.p + 1e-6f * sdir, TR_INF);
-                    L.sd[q] = f4(sdir, __int_as_float(pix));
+                    L.sd[q] = f4(sdir, __int_as_float(slot));
                     L.sc_contrib[q] = f4(contrib, 0.0f);
                 }
             }
@@ -118,12 +140,12 @@ __global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level)
         const bool is_diffuse = num_components(lobes, LB_DIFFUSE | LB_REFLECTION | LB_TRANSMISSION) > 0;
         const bool is_glossy = num_components(lobes, LB_GLOSSY | LB_REFLECTION | LB_TRANSMISSION) > 0;
         if (is_diffuse || (is_glossy && level == L.max_depth)) {
-            const float r = L.tau_r[pix].w;
-            L.vpA[pix] = f4(it.p, r * r);
-            L.vpB[pix] = f4(wo, __uint_as_float(it.material));
-            L.vpC[pix] = f4(fr.ns, is_black3(beta) ? 0.0f : 1.0f);
-            L.vpD[pix] = f4(fr.ss, 0.0f);
-            L.vpE[pix] = f4(fr.ng, 0.0f);
+            const float r = L.tau_r[slot].w;
+            L.vpA[slot] = f4(it.p, r * r);
+            L.vpB[slot] = f4(wo, __uint_as_float(it.material));
+            L.vpC[slot] = f4(fr.ns, is_black3(beta) ? 0.0f : 1.0f);
+            L.vpD[slot] = f4(fr.ss, 0.0f);
+            L.vpE[slot] = f4(fr.ng, 0.0f);
             continue;
         }
         if (level == L.max_depth) continue;
@@ -139,8 +161,8 @@ __global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level)
         }
         const int q = queue_claim(&L.counters[level + 1]);
         L.ro[nxt][q] = f4(it.p + 1e-6f * bs.wi, TR_INF);
-        L.rd[nxt][q] = f4(bs.wi, __int_as_float(pix));
-        L.rw[nxt][q] = f4(beta, 0.0f);
+        L.rd[nxt][q] = f4(bs.wi, __int_as_float(slot));
+        L.rw[nxt][q] = f4(beta, __int_as_float(pix));
     }
 }
 
@@ -159,7 +181,7 @@ __global__ void k_grid_reset(GridParams* g) {
 
 __global__ void __launch_bounds__(256) k_grid_bounds(SppmLaunch L) {
     float lo[3] = {TR_INF, TR_INF, TR_INF}, hi[3] = {-TR_INF, -TR_INF, -TR_INF}, mr = 0.0f;
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.nstore; pix += gridDim.x * blockDim.x) {
         if (L.vpC[pix].w == 0.0f) continue;                       // is_black(vp.beta)
         const float4 A = L.vpA[pix];
         const float r = L.tau_r[pix].w;
@@ -220,7 +242,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) k_grid_insert(SppmLaunch L) {
     const GridParams g = *L.grid;
     if (!g.valid) return;
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.nstore; pix += gridDim.x * blockDim.x) {
         if (L.vpC[pix].w == 0.0f) continue;
         const float4 A = L.vpA[pix];
         const float r = L.tau_r[pix].w;
@@ -407,7 +429,7 @@ __global__ void __launch_bounds__(128) k_photon_deposit(SppmLaunch L, int level)
 // ---------------------------------------------------------------- per-iteration update and image (sppm.jl:438-472)
 __global__ void __launch_bounds__(256) k_sppm_update(SppmLaunch L) {
     const float gamma = 2.0f / 3.0f;
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.nstore; pix += gridDim.x * blockDim.x) {
         const float4 fl = L.flux[pix];
         if (fl.w > 0.0f) {
             float4 tr = L.tau_r[pix];
@@ -431,7 +453,8 @@ __global__ void __launch_bounds__(256) k_sppm_update(SppmLaunch L) {
 __global__ void __launch_bounds__(256) k_sppm_image(SppmLaunch L, int iteration, float* __restrict__ rgb) {
     const double Np = (double)iteration * (double)L.photons_per_iteration * 3.141592653589793;
     for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
-        const float4 ld = L.Ld[pix], tr = L.tau_r[pix];
+        const int st = raster_to_storage(L, pix % L.W, pix / L.W);
+        const float4 ld = L.Ld[st], tr = L.tau_r[st];
         const double den = Np * (double)(tr.w * tr.w);
         rgb[3 * pix + 0] = ld.x / (float)iteration + (float)((double)tr.x / den);
         rgb[3 * pix + 1] = ld.y / (float)iteration + (float)((double)tr.y / den);
@@ -440,7 +463,7 @@ __global__ void __launch_bounds__(256) k_sppm_image(SppmLaunch L, int iteration,
 }
 
 __global__ void k_sppm_init(SppmLaunch L, float r0) {
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.nstore; pix += gridDim.x * blockDim.x) {
         L.Ld[pix] = make_float4(0, 0, 0, 0);
         L.flux[pix] = make_float4(0, 0, 0, 0);
         L.tau_r[pix] = make_float4(0, 0, 0, r0);
@@ -507,11 +530,15 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     ctx_device_camera(cam, &L.cam);
     if (ctx_device_film(c, film, &L.film, &s->table)) return 1;
     L.W = L.film.width; L.H = L.film.height; L.npix = L.W * L.H;
+    if (c->rank < 0 || c->rank >= c->world) { sppm_free(c); return c->fail("rank %d outside world %d", c->rank, c->world); }
+    L.world = c->world; L.rank = c->rank;
+    L.chunk_rows = (L.H + L.world - 1) / L.world;
+    L.nstore = L.world * L.chunk_rows * L.W;
     if (photons <= 0) photons = (int64_t)(film->crop_x1 - film->crop_x0) * (film->crop_y1 - film->crop_y0);   // area(crop_bounds), Q22
     L.photons_per_iteration = photons;
     L.max_depth = max_depth; L.seed = seed; L.iteration = 0;
     s->r0 = r0;
-    const size_t np = (size_t)L.npix;
+    const size_t np = (size_t)L.nstore;
     const size_t f4b = np * sizeof(float4);
     for (int k = 0; k < 8; ++k) TR_CUDA(c, s->pix[k].ensure(f4b));
     TR_CUDA(c, s->pix[8].ensure(np * sizeof(double)));
@@ -606,7 +633,20 @@ extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
     launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
                   (const int*)(ic + 32), L.cap_shadow, L.Ld, st + ST_NODES, ic + IC_ERROR);
     k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap, 1);
-    // hash grid of the visible points: bounds -> resolution -> count -> scan -> fill
+    c->stats.kernel_launches++;
+    TR_CUDA(c, cudaGetLastError());
+    if (c->world > 1) return check_flags(c, "trace_sppm_camera_pass");   // caller all-gathers the visible points, then build_grid
+    return trace_sppm_build_grid(c);
+}
+
+// hash grid of the visible points (sppm.jl:272-318): bounds -> resolution -> count -> scan -> fill
+extern "C" int trace_sppm_build_grid(trace_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_build_grid: call trace_sppm_begin first");
+    SppmState* s = c->sppm;
+    SppmLaunch& L = s->L;
+    const int g_stream = persistent_grid(c, 8);
     const int n_cells = L.npix + 1;
     const int scan_blocks = (n_cells + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
     k_grid_reset<<<1, 1, 0, c->stream>>>(L.grid);
@@ -621,7 +661,7 @@ extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
     k_grid_insert<true><<<g_stream, 256, 0, c->stream>>>(L);
     c->stats.kernel_launches += 10;
     TR_CUDA(c, cudaGetLastError());
-    return check_flags(c, "trace_sppm_camera_pass");
+    return check_flags(c, "trace_sppm_build_grid");
 }
 
 extern "C" int trace_sppm_photon_pass(trace_ctx* c, int iteration, int64_t begin, int64_t end) {
@@ -659,10 +699,25 @@ extern "C" int trace_sppm_photon_pass(trace_ctx* c, int iteration, int64_t begin
     return 0;
 }
 
-extern "C" void* trace_sppm_flux_device(trace_ctx* c, int64_t* n_floats) {
+extern "C" void* trace_sppm_flux_device(trace_ctx* c, int64_t* n_floats) { return trace_sppm_buffer_device(c, 0, n_floats); }
+
+// Per-pixel device buffers in STORAGE order (rank r owns the contiguous slice [r, r+1) * n_floats / world):
+// 0 flux (Phi.rgb, M) - all-reduce(sum) after the photon pass; 1 Ld - all-gather before the image;
+// 2..6 visible-point records - all-gather after the camera pass.
+extern "C" void* trace_sppm_buffer_device(trace_ctx* c, int which, int64_t* n_floats) {
     if (!c || !c->sppm) return nullptr;
-    if (n_floats) *n_floats = (int64_t)c->sppm->L.npix * 4;
-    return c->sppm->L.flux;
+    SppmLaunch& L = c->sppm->L;
+    if (n_floats) *n_floats = (int64_t)L.nstore * 4;
+    switch (which) {
+        case 0: return L.flux;
+        case 1: return L.Ld;
+        case 2: return L.vpA;
+        case 3: return L.vpB;
+        case 4: return L.vpC;
+        case 5: return L.vpD;
+        case 6: return L.vpE;
+        default: return nullptr;
+    }
 }
 
 extern "C" int trace_sppm_update(trace_ctx* c) {

@@ -4,9 +4,11 @@ exchange steps the path has:
   * Whitted: 16x16 sample tiles are dealt round-robin to the ranks (tile k -> rank k % world, the reference's
     Threads.@threads loop over tiles, src/integrators/sampler.jl:24); every rank splats into a private full-resolution
     film; ONE reduce(sum) of the (X, Y, Z, w) film at the end.
-  * SPPM: every rank runs the identical camera pass (same counter-based RNG -> identical visible points and grid),
-    traces its slice of the iteration's photons (Halton index range, src/integrators/sppm.jl:328-336) into a private
-    (Phi, M) buffer, ONE all_reduce(sum) of that buffer per iteration, then the identical per-pixel update.
+  * SPPM: the camera pass is sharded by image rows (row y -> rank y % world; the RNG is keyed by the raster pixel, so
+    the visible points do not depend on the rank count) and the visible-point records are all-gathered (5 float4
+    arrays); every rank then builds the identical hash grid, traces its slice of the iteration's photons (Halton index
+    range, src/integrators/sppm.jl:328-336) into a private (Phi, M) buffer, ONE all_reduce(sum) of that buffer per
+    iteration, then the identical per-pixel update.  Ld stays sharded until the image is assembled (one all-gather).
 
 The host-side partition helpers are pure Python so they can be tested with gloo on CPU.
 """
@@ -79,25 +81,44 @@ class SPPMSession:
             photons_per_iteration = int(camera.film.crop_bounds.area())
         self.photons = int(photons_per_iteration)
         cam, fd = camera.pod(), camera.film.desc()
+        ctx.set_option("world", world)
+        ctx.set_option("rank", rank)
         ctx.check(ctx.lib.trace_sppm_begin(ctx.h, C.byref(cam), C.byref(fd), float(initial_search_radius), int(max_depth),
                                            self.photons, C.c_uint64(seed)))
-        n = C.c_int64()
-        ptr = ctx.lib.trace_sppm_flux_device(ctx.h, C.byref(n))
-        self.flux = torch.as_tensor(_DevicePtr(ptr, n.value), device=f"cuda:{torch.cuda.current_device()}") if world > 1 else None
+        self.buffers = None
+        if world > 1:
+            dev = f"cuda:{torch.cuda.current_device()}"
+            self.buffers = []
+            for which in range(7):          # 0 flux, 1 Ld, 2..6 visible-point records (storage order, rank-major slices)
+                n = C.c_int64()
+                ptr = ctx.lib.trace_sppm_buffer_device(ctx.h, which, C.byref(n))
+                self.buffers.append(torch.as_tensor(_DevicePtr(ptr, n.value), device=dev))
         self.iteration = 0
+
+    def _all_gather(self, which):
+        import torch.distributed as dist
+        t = self.buffers[which]
+        n = t.numel() // self.world
+        dist.all_gather_into_tensor(t, t[self.rank * n:(self.rank + 1) * n].clone(), group=self.group)
 
     def step(self):
         """One SPPM iteration (sppm.jl:153-165) over all ranks."""
         self.iteration += 1
         ctx = self.ctx
         ctx.check(ctx.lib.trace_sppm_camera_pass(ctx.h, self.iteration))
+        if self.world > 1:
+            for which in range(2, 7):
+                self._all_gather(which)
+            ctx.check(ctx.lib.trace_sppm_build_grid(ctx.h))
         b, e = photon_range(self.photons, self.rank, self.world)
         ctx.check(ctx.lib.trace_sppm_photon_pass(ctx.h, self.iteration, b, e))
         if self.world > 1:
-            allreduce_sum(self.flux, self.group)
+            allreduce_sum(self.buffers[0], self.group)
         ctx.check(ctx.lib.trace_sppm_update(ctx.h))
 
     def image(self):
+        if self.world > 1:
+            self._all_gather(1)             # Ld is accumulated only by the rank that owns the row
         h, w = self.camera.film.pixels.shape[:2]
         rgb = np.zeros((h, w, 3), dtype=np.float32)
         self.ctx.check(self.ctx.lib.trace_sppm_image(self.ctx.h, max(1, self.iteration), _lib.ptr(rgb)))
