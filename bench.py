@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--persist", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=12)
+    ap.add_argument("--graph", type=int, default=1, help="replay the render as one CUDA graph (0: direct launches)")
     ap.add_argument("--ref-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sppm", action="store_true")
@@ -166,11 +167,15 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = T.Context(local, stream=stream)
+    # one non-default torch stream for everything: the library's launches, torch's fills, NCCL's ordering and the CUDA
+    # events below all see the same stream (torch's default stream has handle 0, which the library takes as "make your own")
+    work_stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(work_stream)
+    ctx = T.Context(local, stream=work_stream.cuda_stream)
     ctx.set_option("slab", args.slab)
     ctx.set_option("persist", args.persist)
     ctx.set_option("lanes", args.lanes)
+    ctx.set_option("graph", args.graph)
     if args.batch:
         ctx.set_option("batch", args.batch)
 

@@ -188,7 +188,9 @@ int trace_render_sppm(trace_ctx* ctx, const trace_camera* cam, const trace_film_
                       int write_frequency, uint64_t seed, trace_sppm_cb on_image, void* user,
                       float* rgb_out /* [crop_h][crop_w][3], image after the last iteration (sppm.jl:461-472) */);
 /* stepwise form used for multi-GPU sharding (options "rank"/"world" set BEFORE trace_sppm_begin): begin; per iteration
- * { camera_pass (this rank's image rows; with world == 1 it also builds the grid);
+ * { [trace_photons(this rank's photon range): optional, asynchronous - the photon paths (sppm.jl:328-434 minus the
+ *    deposits) then overlap the camera pass and the all-gather];
+ *   camera_pass (this rank's image rows; with world == 1 it also builds the grid);
  *   [world > 1: all-gather buffers 2..6, then trace_sppm_build_grid];
  *   photon_pass(this rank's photon range); [world > 1: all-reduce(sum) buffer 0]; update };
  * [world > 1: all-gather buffer 1]; image; end.  Per-pixel buffers are in storage order: image rows dealt round-robin
@@ -196,6 +198,7 @@ int trace_render_sppm(trace_ctx* ctx, const trace_camera* cam, const trace_film_
 int   trace_sppm_begin(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film,
                        float initial_radius, int max_depth, int64_t photons_per_iteration, uint64_t seed);
 int   trace_sppm_camera_pass(trace_ctx* ctx, int iteration);
+int   trace_sppm_trace_photons(trace_ctx* ctx, int iteration, int64_t photon_begin, int64_t photon_end);
 int   trace_sppm_photon_pass(trace_ctx* ctx, int iteration, int64_t photon_begin, int64_t photon_end);
 int   trace_sppm_build_grid(trace_ctx* ctx);
 void* trace_sppm_flux_device(trace_ctx* ctx, int64_t* n_floats /* 4 per pixel slot: Phi.rgb, M */);

@@ -10,7 +10,10 @@ res = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 kw_res = dict(resolution=res) if res else {}
 scene, camera, kw = getattr(T.scenes, name)(**kw_res)
 torch.cuda.set_device(0)
-ctx = T.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+_s = torch.cuda.Stream(device=0)
+torch.cuda.set_stream(_s)
+ctx = T.Context(0, stream=_s.cuda_stream)
+ctx.set_option("sppm_lanes", int(os.environ.get("SPPM_LANES", "0")))
 sess = D.SPPMSession(ctx, scene, camera, kw["initial_search_radius"], kw["max_depth"], kw.get("photons_per_iteration", -1))
 for _ in range(2):
     sess.step()
@@ -24,7 +27,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 st = ctx.stats()
-print(f"{name}: {iters / ms * 1e3:.2f} it/s  ({ms / iters:.3f} ms/it)  rays/it extend {st['rays_extend'] / iters:.0f} shadow {st['rays_shadow'] / iters:.0f} "
+print(f"{name} sppm_lanes={os.environ.get('SPPM_LANES', '0')}: {iters / ms * 1e3:.2f} it/s  ({ms / iters:.3f} ms/it)  rays/it extend {st['rays_extend'] / iters:.0f} shadow {st['rays_shadow'] / iters:.0f} "
       f"deposits/it {st['sppm_deposits'] / iters:.0f} launches/it {st['kernel_launches'] / iters:.1f} photons/it {sess.photons}")
 img = sess.image()
 print("image mean", float(img.mean()), "max", float(img.max()))

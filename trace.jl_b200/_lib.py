@@ -85,6 +85,7 @@ SIGNATURES = {
                                     C.c_int, C.c_uint64, SPPM_CB, _P, _P]),
     "trace_sppm_begin": (C.c_int, [_P, C.POINTER(Camera), C.POINTER(FilmDesc), C.c_float, C.c_int, C.c_int64, C.c_uint64]),
     "trace_sppm_camera_pass": (C.c_int, [_P, C.c_int]),
+    "trace_sppm_trace_photons": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64]),
     "trace_sppm_photon_pass": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64]),
     "trace_sppm_build_grid": (C.c_int, [_P]),
     "trace_sppm_flux_device": (_P, [_P, C.POINTER(C.c_int64)]),

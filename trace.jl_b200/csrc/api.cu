@@ -79,6 +79,7 @@ extern "C" void trace_destroy(trace_ctx* c) {
     for (auto& e : c->kev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int l = 0; l < trace_ctx::MAX_LANES; ++l) { if (c->side[l]) cudaStreamDestroy(c->side[l]); if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->wh_graph) cudaGraphExecDestroy(c->wh_graph);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -99,6 +100,9 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "lanes")) { if (v < 1 || v > trace_ctx::MAX_LANES) return c->fail("lanes must be in [1, 16]"); c->lanes = (int)v; }
     else if (!strcmp(key, "cap_percent")) { if (v < 100 || v > 1600) return c->fail("cap_percent must be in [100, 1600]"); c->cap_percent = (int)v; }
     else if (!strcmp(key, "time_kernels")) c->time_kernels = v != 0;
+    else if (!strcmp(key, "graph")) c->graph = v != 0;
+    else if (!strcmp(key, "sppm_lanes")) { if (v < 0 || v > trace_ctx::MAX_LANES / 2) return c->fail("sppm_lanes must be in [0, 8]"); c->sppm_lanes = (int)v; }
+    else if (!strcmp(key, "deal")) c->deal = (int)v;
     else if (!strcmp(key, "rank")) c->rank = (int)v;
     else if (!strcmp(key, "world")) { if (v < 1) return c->fail("world must be >= 1"); c->world = (int)v; }
     else return c->fail("unknown option '%s'", key);

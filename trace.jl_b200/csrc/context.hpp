@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -52,6 +53,15 @@ struct trace_ctx {
     int work_slot = 0;
     int time_kernels = 0;
     int rank = 0, world = 1;
+    // CUDA graph of one Whitted render (all lanes, all batches): a render is ~20 launches per batch and the host
+    // needs ~4.5 us per launch, which bounds small renders (1/8 of a frame per GPU) - replaying a captured graph does
+    // not.  Keyed by every launch parameter; camera and seed live in a device block so they may change between replays
+    int graph = 1;
+    int sppm_lanes = 0;           // sub-ranges of each SPPM pass on concurrent streams (0: by scene size)
+    int deal = -2;                // groups of tiles dealt round-robin to the batches: g > 0 tiles, -r: r tile rows, 0: contiguous bands
+    cudaGraphExec_t wh_graph = nullptr;
+    std::string wh_graph_key;
+    unsigned long long wh_graph_launches[3] = {0, 0, 0};   // kernel / extend / shadow launches one replay stands for
 
     // scene
     bool have_scene = false;
@@ -68,13 +78,14 @@ struct trace_ctx {
     trace_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     // per-launch CUDA-event timing of the traversal kernels (option "time_kernels"), resolved after a stream sync
-    struct KernelEvent { cudaEvent_t a, b; int kind; };
+    struct KernelEvent { cudaEvent_t a, b; int kind, lane; };
     std::vector<KernelEvent> kev;
     size_t kev_used = 0;
     void kev_begin(int kind) {
         if (!time_kernels) return;
         if (kev_used == kev.size()) { KernelEvent e; cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.kind = kind; kev.push_back(e); }
         kev[kev_used].kind = kind;
+        kev[kev_used].lane = cur_lane;
         cudaEventRecord(kev[kev_used].a, cur_stream);
     }
     void kev_end() {
@@ -83,13 +94,24 @@ struct trace_ctx {
         kev_used++;
     }
     void kev_collect() {      // call after the stream has been synchronised
+        // debugging aid: TRACE_CUDA_TIMELINE=<file> appends "lane kind start_ms end_ms" (relative to the render's start
+        // event) for every timed traversal launch - a poor man's timeline of how the lanes overlap
+        const char* tl_path = getenv("TRACE_CUDA_TIMELINE");
+        FILE* tl = (tl_path && kev_used) ? fopen(tl_path, "a") : nullptr;
+        if (tl) fprintf(tl, "# render\n");
         for (size_t i = 0; i < kev_used; ++i) {
             float ms = 0.0f;
+            if (tl) {
+                float t0 = 0.0f, t1 = 0.0f;
+                if (cudaEventElapsedTime(&t0, ev0, kev[i].a) == cudaSuccess && cudaEventElapsedTime(&t1, ev0, kev[i].b) == cudaSuccess)
+                    fprintf(tl, "%d %d %.4f %.4f\n", kev[i].lane, kev[i].kind, t0, t1);
+            }
             if (cudaEventElapsedTime(&ms, kev[i].a, kev[i].b) == cudaSuccess) {
                 if (kev[i].kind == 0) { stats.ms_extend += ms; stats.extend_launches++; }
                 else { stats.ms_shadow += ms; stats.shadow_launches++; }
             }
         }
+        if (tl) fclose(tl);
         kev_used = 0;
     }
 

@@ -47,9 +47,11 @@ struct SppmLaunch {
     // queues
     float4 *ro[2], *rd[2], *rw[2], *hits;
     float4 *so, *sd, *sc_contrib;
-    int* counters;
+    int* counters;             // this lane's queue counters
+    int* flags;                // [IC_OVERFLOW], [IC_ERROR]: one pair for the whole session (lane 0's block)
     int cap;
     int cap_shadow;            // shadow-ray queue (camera pass) / deposit-request queue (photon pass): all levels share it
+    int range_begin, range_end;   // camera pass: the storage slots this lane generates paths for
     // photons
     long long photon_begin;    // first photon index (within the iteration) of this launch
     int n_photons;
@@ -74,8 +76,7 @@ __device__ __forceinline__ int raster_to_storage(const SppmLaunch& L, int x, int
 // One camera path per pixel of THIS rank's rows (sppm.jl:184-196). The RNG is keyed by the raster pixel index, so the
 // visible points do not depend on the number of ranks.
 __global__ void __launch_bounds__(256) k_sppm_cam_generate(SppmLaunch L) {
-    const int s0 = L.rank * L.chunk_rows * L.W, s1 = s0 + L.chunk_rows * L.W;
-    for (int st = s0 + blockIdx.x * blockDim.x + threadIdx.x; st < s1; st += gridDim.x * blockDim.x) {
+    for (int st = L.range_begin + blockIdx.x * blockDim.x + threadIdx.x; st < L.range_end; st += gridDim.x * blockDim.x) {
         int x, y;
         if (!storage_to_raster(L, st, x, y)) continue;
         const int pix = y * L.W + x;      // raster index: RNG key
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level)
                     const float3 contrib = ((f * Li) / 1.0f) / light_pdf;
                     const float3 sdir = lpos - it.p;
                     const int q = queue_claim(&L.counters[32]);
-                    if (q >= L.cap_shadow) { L.counters[IC_OVERFLOW] = 1; continue; }
+                    if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW] = 1; continue; }
                     L.so[q] = f4(it.p + 1e-6f * sdir, TR_INF);
                     L.sd[q] = f4(sdir, __int_as_float(slot));
                     L.sc_contrib[q] = f4(contrib, 0.0f);
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(unsigned int* data, int
     for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) { unsigned int v = data[base + k] + add; data[base + k] = v; cursor[base + k] = v; }
 }
 __global__ void k_grid_check(SppmLaunch L) {
-    if (L.grid->total_items > L.items_cap) L.counters[IC_OVERFLOW] = 1;
+    if (L.grid->total_items > L.items_cap) L.flags[IC_OVERFLOW] = 1;
     L.cell_start[L.npix] = L.grid->total_items;
 }
 
@@ -352,19 +353,13 @@ __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
         const Interaction it = build_interaction(L.sc, prim, xyz(o4), d, h.z, h.w, b2);
         const float3 wo = -d;
         if (level > 1) {
-            // photon landed at depth > 1: queue a deposit request for k_photon_deposit (sppm.jl:377-403)
-            const GridParams& g = *L.grid;
-            int cell[3];
-            if (g.valid && to_grid(g, it.p, cell)) {
-                const unsigned int hsh = grid_hash(cell[0], cell[1], cell[2], (unsigned int)L.npix);
-                if (L.cell_start[hsh + 1] > L.cell_start[hsh]) {
-                    const int q = queue_claim(&L.counters[32]);
-                    if (q >= L.cap_shadow) { L.counters[IC_OVERFLOW] = 1; continue; }
-                    L.so[q] = f4(it.p, __uint_as_float(hsh));
-                    L.sd[q] = f4(wo, 0.0f);
-                    L.sc_contrib[q] = f4(beta, 0.0f);
-                }
-            }
+            // photon landed at depth > 1: queue a deposit request for k_photon_deposit (sppm.jl:377-403).  The grid is
+            // NOT consulted here - it is being rebuilt by the concurrent camera pass; the deposit kernel does the lookup
+            const int q = queue_claim(&L.counters[32]);
+            if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW] = 1; continue; }
+            L.so[q] = f4(it.p, 0.0f);
+            L.sd[q] = f4(wo, 0.0f);
+            L.sc_contrib[q] = f4(beta, 0.0f);
         }
         const Frame fr = make_frame(it);
         LobeSet lobes;
@@ -400,12 +395,17 @@ __global__ void __launch_bounds__(128) k_photon_deposit(SppmLaunch L, int level)
     // TR_DEPOSIT_SPLIT warps share one request (interleaved 32-entry slices of its list): a request's chain of
     // dependent gathers is 8x shorter and there are 8x more independent tasks to hide latency with
     const long long n_tasks = (long long)n * TR_DEPOSIT_SPLIT;
+    const GridParams g = *L.grid;
+    if (!g.valid) return;
     for (long long task = warp; task < n_tasks; task += n_warps) {
         const int r = (int)(task / TR_DEPOSIT_SPLIT), sub = (int)(task % TR_DEPOSIT_SPLIT);
-        const float4 P = L.so[r], WO = L.sd[r], B = L.sc_contrib[r];
-        const float3 p = xyz(P), wo = xyz(WO), beta = xyz(B);
-        const unsigned int hsh = __float_as_uint(P.w);
+        const float3 p = xyz(L.so[r]);
+        int cell[3];
+        if (!to_grid(g, p, cell)) continue;
+        const unsigned int hsh = grid_hash(cell[0], cell[1], cell[2], (unsigned int)L.npix);
         const unsigned int e0 = L.cell_start[hsh], e1 = L.cell_start[hsh + 1];
+        if (e0 + sub * 32 >= e1) continue;
+        const float3 wo = xyz(L.sd[r]), beta = xyz(L.sc_contrib[r]);
         for (unsigned int e = e0 + sub * 32 + lane; e < e1; e += 32 * TR_DEPOSIT_SPLIT) {
             const float4 A = __ldcs(&L.cell_vp[e]);                  // streamed once per request: keep it out of L1
             const float3 dd = xyz(A) - p;
@@ -478,17 +478,26 @@ __global__ void k_sppm_stats(int* counters, unsigned long long* stats, int max_d
         unsigned long long e = 0, s = 0;
         for (int l = 1; l <= max_depth; ++l) e += min(counters[l], cap);
         s = counters[32];
-        stats[ST_RAYS_EXTEND] += e;
-        if (count_shadow) stats[ST_RAYS_SHADOW] += s;      // in the photon pass slots 32.. count deposit requests
+        atomicAdd(&stats[ST_RAYS_EXTEND], e);              // (lanes run concurrently)
+        if (count_shadow) atomicAdd(&stats[ST_RAYS_SHADOW], s);      // in the photon pass slots 32.. count deposit requests
     }
 }
 
 // ---------------------------------------------------------------- host side
+// Lanes: the camera pass and the photon pass are chains of ~12 dependent launches whose traversal launches cannot end
+// before their slowest ray (0.2-0.5 ms in the 88k-triangle glass block, whatever the ray count).  Photon TRACING does
+// not need the grid - only the deposits do - so it runs on its own streams concurrently with the camera pass, and each
+// pass is cut into `K` sub-ranges on separate streams whose latency-bound tails overlap.
 struct SppmState {
     SppmLaunch L;
-    DevBuf pix[10], grid, cells[4], scan_sums, q[10], table, lights;
+    DevBuf pix[10], grid, cells[4], scan_sums, q[10], pq[10], table, lights;
     float r0;
-    int photon_cap;
+    int photon_cap;                 // photons one lane can hold
+    int Kc = 1, Kp = 1;             // camera lanes use the context's lane ids 0..Kc-1, photon lanes Kc..Kc+Kp-1
+    std::vector<SppmLaunch> cam_lane, ph_lane;
+    cudaEvent_t ev_ph_fork = nullptr, ev_grid = nullptr;
+    int traced_it = -1;             // photon tracing already enqueued for this iteration / range
+    int64_t traced_begin = 0, traced_end = 0;
     bool active = false;
 };
 
@@ -498,6 +507,9 @@ void sppm_free(trace_ctx* c) {
     for (auto& b : s->pix) b.release();
     for (auto& b : s->cells) b.release();
     for (auto& b : s->q) b.release();
+    for (auto& b : s->pq) b.release();
+    if (s->ev_ph_fork) cudaEventDestroy(s->ev_ph_fork);
+    if (s->ev_grid) cudaEventDestroy(s->ev_grid);
     s->grid.release(); s->scan_sums.release(); s->table.release(); s->lights.release();
     delete s;
     c->sppm = nullptr;
@@ -557,18 +569,41 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     L.cell_items = s->cells[2].as<unsigned int>();
     const int scan_blocks = (int)((np + 1 + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS));
     TR_CUDA(c, s->scan_sums.ensure((size_t)scan_blocks * sizeof(unsigned int)));
-    // queues sized for max(npix, photon chunk)
-    s->photon_cap = (int)std::min<int64_t>(photons, std::max<int64_t>(c->batch * 2, 1 << 20));
-    const size_t cap = std::max<size_t>(np, (size_t)s->photon_cap);
-    L.cap = (int)cap;
-    L.cap_shadow = (int)std::min<size_t>(cap * (size_t)max_depth, (size_t)1 << 30);
-    for (int k = 0; k < 7; ++k) TR_CUDA(c, s->q[k].ensure(cap * sizeof(float4)));
-    for (int k = 7; k < 10; ++k) TR_CUDA(c, s->q[k].ensure((size_t)L.cap_shadow * sizeof(float4)));
-    L.ro[0] = s->q[0].as<float4>(); L.ro[1] = s->q[1].as<float4>(); L.rd[0] = s->q[2].as<float4>(); L.rd[1] = s->q[3].as<float4>();
-    L.rw[0] = s->q[4].as<float4>(); L.rw[1] = s->q[5].as<float4>(); L.hits = s->q[6].as<float4>();
-    L.so = s->q[7].as<float4>(); L.sd = s->q[8].as<float4>(); L.sc_contrib = s->q[9].as<float4>();
-    L.counters = ctx_icounters(c);
+    // one camera lane + one photon lane by default: measured on B200, cutting the passes further (sppm_lanes 2/4/8) only
+    // adds launches - the traversal launches of these scenes are throughput-bound (the glass block's degenerate BVH
+    // costs every ray ~1000 node visits), not bound by a few slow rays (profiles/r1_experiments.md)
+    const int K = c->sppm_lanes > 0 ? c->sppm_lanes : 1;
+    s->Kc = s->Kp = std::min(K, trace_ctx::MAX_LANES / 2);
+    TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_ph_fork, cudaEventDisableTiming));
+    TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_grid, cudaEventDisableTiming));
+    // camera queues hold this rank's pixels, photon queues one chunk of photons; both are cut evenly over the lanes
+    const size_t rank_slots = (size_t)L.chunk_rows * L.W;
+    const size_t cam_cap = (rank_slots + s->Kc - 1) / s->Kc;
+    const size_t ph_total = (size_t)std::min<int64_t>(photons, std::max<int64_t>(c->batch * 2, 1 << 20));
+    const size_t ph_cap = (ph_total + s->Kp - 1) / s->Kp;
+    s->photon_cap = (int)ph_cap;
+    L.counters = ctx_icounters_lane(c, 0);
+    L.flags = ctx_icounters_lane(c, 0);
     L.stats = ctx_stats64(c);
+    L.cap = 0; L.cap_shadow = 0; L.range_begin = L.range_end = 0;
+    auto carve = [&](DevBuf* q, int K_, size_t cap, std::vector<SppmLaunch>& lanes, int lane0) -> int {
+        const size_t cap_sh = std::min<size_t>(cap * (size_t)max_depth, (size_t)1 << 30);
+        for (int k = 0; k < 7; ++k) TR_CUDA(c, q[k].ensure((size_t)K_ * cap * sizeof(float4)));
+        for (int k = 7; k < 10; ++k) TR_CUDA(c, q[k].ensure((size_t)K_ * cap_sh * sizeof(float4)));
+        lanes.assign((size_t)K_, L);
+        for (int l = 0; l < K_; ++l) {
+            SppmLaunch& W = lanes[l];
+            W.ro[0] = q[0].as<float4>() + l * cap; W.ro[1] = q[1].as<float4>() + l * cap;
+            W.rd[0] = q[2].as<float4>() + l * cap; W.rd[1] = q[3].as<float4>() + l * cap;
+            W.rw[0] = q[4].as<float4>() + l * cap; W.rw[1] = q[5].as<float4>() + l * cap;
+            W.hits = q[6].as<float4>() + l * cap;
+            W.so = q[7].as<float4>() + l * cap_sh; W.sd = q[8].as<float4>() + l * cap_sh; W.sc_contrib = q[9].as<float4>() + l * cap_sh;
+            W.cap = (int)cap; W.cap_shadow = (int)cap_sh;
+            W.counters = ctx_icounters_lane(c, lane0 + l);
+        }
+        return 0;
+    };
+    // (lanes are carved again below, once the light tables are in L)
     // light power distribution: Distribution1D (sampling.jl:3-30), built on the host from the uploaded lights
     const int nl = c->scene.n_lights;
     std::vector<DeviceLight> hl((size_t)nl);
@@ -591,6 +626,12 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     TR_CUDA(c, cudaMemcpyAsync(s->lights.p, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
     L.light_cdf = s->lights.as<float>(); L.light_func = s->lights.as<float>() + nl + 1; L.light_func_int = func_int;
+    if (carve(s->q, s->Kc, cam_cap, s->cam_lane, 0) || carve(s->pq, s->Kp, ph_cap, s->ph_lane, s->Kc)) return 1;
+    for (int l = 0; l < s->Kc; ++l) {
+        const size_t s0 = (size_t)L.rank * rank_slots;
+        s->cam_lane[l].range_begin = (int)(s0 + std::min(rank_slots, (size_t)l * cam_cap));
+        s->cam_lane[l].range_end = (int)(s0 + std::min(rank_slots, (size_t)(l + 1) * cam_cap));
+    }
     k_sppm_init<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L, r0);
     c->stats.kernel_launches++;
     TR_CUDA(c, cudaGetLastError());
@@ -608,32 +649,59 @@ static int check_flags(trace_ctx* c, const char* what) {
     return 0;
 }
 
+// Runs `body(lane)` for every lane on its own side stream (forked from / joined into the main stream), or directly on
+// the main stream when there is only one lane and `fork_event` is null.
+struct LaneScope {
+    trace_ctx* c;
+    LaneScope(trace_ctx* c_, int lane, cudaStream_t st) : c(c_) { c->cur_lane = lane; c->cur_stream = st; }
+    ~LaneScope() { c->cur_lane = 0; c->cur_stream = c->stream; }
+};
+
+static int sppm_camera_lane(trace_ctx* c, SppmState* s, int l, int iteration) {
+    SppmLaunch& W = s->cam_lane[l];
+    W.iteration = iteration;
+    cudaStream_t st = c->cur_stream;
+    int* ic = W.counters;
+    unsigned long long* stats = ctx_stats64(c);
+    TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), st));
+    TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), st)); c->work_slot = 0;
+    const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
+    k_sppm_cam_generate<<<g_stream, 256, 0, st>>>(W);
+    c->stats.kernel_launches++;
+    for (int level = 1; level <= W.max_depth; ++level) {
+        const int cur = (level - 1) & 1;
+        launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
+                      stats + ST_NODES, W.flags + IC_ERROR);
+        k_sppm_cam_shade<<<occupancy_grid(c, k_sppm_cam_shade, 128), 128, 0, st>>>(W, level);
+        c->stats.kernel_launches++;
+    }
+    // shadow rays of all levels in one any-hit launch (they only feed Ld)
+    launch_shadow(c, g_trav, W.sc, (const float4*)W.so, (const float4*)W.sd, (const float4*)W.sc_contrib,
+                  (const int*)(ic + 32), W.cap_shadow, W.Ld, stats + ST_NODES, W.flags + IC_ERROR);
+    k_sppm_stats<<<1, 32, 0, st>>>(ic, stats, W.max_depth, W.cap, 1);
+    c->stats.kernel_launches++;
+    return 0;
+}
+
 extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
     if (!c) return 1;
     cudaSetDevice(c->device);
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_camera_pass: call trace_sppm_begin first");
     SppmState* s = c->sppm;
-    SppmLaunch& L = s->L;
-    L.iteration = iteration;
-    int* ic = ctx_icounters(c);
-    unsigned long long* st = ctx_stats64(c);
-    TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->stream));
-    TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), c->stream)); c->work_slot = 0;
-    const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
-    k_sppm_cam_generate<<<g_stream, 256, 0, c->stream>>>(L);
-    c->stats.kernel_launches++;
-    for (int level = 1; level <= L.max_depth; ++level) {
-        const int cur = (level - 1) & 1;
-        launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap, L.hits,
-                      st + ST_NODES, ic + IC_ERROR);
-        k_sppm_cam_shade<<<occupancy_grid(c, k_sppm_cam_shade, 128), 128, 0, c->stream>>>(L, level);
-        c->stats.kernel_launches++;
+    s->L.iteration = iteration;
+    if (s->Kc == 1) {
+        LaneScope scope(c, 0, c->stream);
+        if (sppm_camera_lane(c, s, 0, iteration)) return 1;
+    } else {
+        TR_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+        for (int l = 0; l < s->Kc; ++l) {
+            TR_CUDA(c, cudaStreamWaitEvent(c->side[l], c->ev_fork, 0));
+            LaneScope scope(c, l, c->side[l]);
+            if (sppm_camera_lane(c, s, l, iteration)) return 1;
+            TR_CUDA(c, cudaEventRecord(c->ev_join[l], c->side[l]));
+            TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[l], 0));
+        }
     }
-    // shadow rays of all levels in one any-hit launch (they only feed Ld)
-    launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
-                  (const int*)(ic + 32), L.cap_shadow, L.Ld, st + ST_NODES, ic + IC_ERROR);
-    k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap, 1);
-    c->stats.kernel_launches++;
     TR_CUDA(c, cudaGetLastError());
     if (c->world > 1) return check_flags(c, "trace_sppm_camera_pass");   // caller all-gathers the visible points, then build_grid
     return trace_sppm_build_grid(c);
@@ -664,36 +732,91 @@ extern "C" int trace_sppm_build_grid(trace_ctx* c) {
     return check_flags(c, "trace_sppm_build_grid");
 }
 
+// Photon tracing of [begin, end) on the photon lanes: generate -> (extend -> shade) x depth.  The shade kernel leaves
+// deposit REQUESTS (hit point, direction, weight) in the lane's request queue; nothing here reads the grid.
+static int sppm_trace_lane(trace_ctx* c, SppmState* s, int j, int iteration, int64_t b, int n) {
+    SppmLaunch& W = s->ph_lane[j];
+    W.iteration = iteration;
+    W.photon_begin = b;
+    W.n_photons = n;
+    cudaStream_t st = c->cur_stream;
+    int* ic = W.counters;
+    unsigned long long* stats = ctx_stats64(c);
+    TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), st));
+    TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), st)); c->work_slot = 0;
+    const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
+    k_photon_generate<<<g_stream, 256, 0, st>>>(W);
+    c->stats.kernel_launches++;
+    for (int level = 1; level <= W.max_depth; ++level) {
+        const int cur = (level - 1) & 1;
+        launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
+                      stats + ST_NODES, W.flags + IC_ERROR);
+        k_photon_shade<<<occupancy_grid(c, k_photon_shade, 128), 128, 0, st>>>(W, level);
+        c->stats.kernel_launches++;
+    }
+    return 0;
+}
+
+static int sppm_deposit_lane(trace_ctx* c, SppmState* s, int j) {
+    SppmLaunch& W = s->ph_lane[j];
+    cudaStream_t st = c->cur_stream;
+    // deposit requests of all bounce levels in one launch (deposits do not feed back into the photon paths)
+    k_photon_deposit<<<occupancy_grid(c, k_photon_deposit, 128), 128, 0, st>>>(W, 0);
+    k_sppm_stats<<<1, 32, 0, st>>>(W.counters, ctx_stats64(c), W.max_depth, W.cap, 0);
+    c->stats.kernel_launches += 2;
+    return 0;
+}
+
+// Starts tracing this iteration's photons [begin, end) WITHOUT depositing them.  Call it before trace_sppm_camera_pass:
+// the photon paths then run concurrently with the camera pass (and with the caller's all-gather of the visible points);
+// trace_sppm_photon_pass(iteration, begin, end) later only joins and deposits.  Optional: photon_pass traces by itself
+// when this was not called (or the range does not fit the photon queues in one go).
+extern "C" int trace_sppm_trace_photons(trace_ctx* c, int iteration, int64_t begin, int64_t end) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_trace_photons: call trace_sppm_begin first");
+    SppmState* s = c->sppm;
+    if (begin < 0 || end > s->L.photons_per_iteration || begin > end) return c->fail("trace_sppm_trace_photons: bad photon range");
+    s->traced_it = -1;
+    if (end - begin > (int64_t)s->photon_cap * s->Kp) return 0;          // does not fit: photon_pass will chunk it
+    const int64_t per = (end - begin + s->Kp - 1) / s->Kp;
+    TR_CUDA(c, cudaEventRecord(s->ev_ph_fork, c->stream));               // after the previous iteration's deposits / update
+    for (int j = 0; j < s->Kp; ++j) {
+        const int lane = s->Kc + j;
+        const int64_t b = std::min(end, begin + j * per), e = std::min(end, b + per);
+        TR_CUDA(c, cudaStreamWaitEvent(c->side[lane], s->ev_ph_fork, 0));
+        LaneScope scope(c, lane, c->side[lane]);
+        if (sppm_trace_lane(c, s, j, iteration, b, (int)(e - b))) return 1;
+    }
+    TR_CUDA(c, cudaGetLastError());
+    s->traced_it = iteration; s->traced_begin = begin; s->traced_end = end;
+    return 0;
+}
+
 extern "C" int trace_sppm_photon_pass(trace_ctx* c, int iteration, int64_t begin, int64_t end) {
     if (!c) return 1;
     cudaSetDevice(c->device);
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_photon_pass: call trace_sppm_begin first");
     SppmState* s = c->sppm;
-    SppmLaunch& L = s->L;
-    if (begin < 0 || end > L.photons_per_iteration || begin > end) return c->fail("trace_sppm_photon_pass: bad photon range");
-    L.iteration = iteration;
-    int* ic = ctx_icounters(c);
-    unsigned long long* st = ctx_stats64(c);
-    const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
-    for (int64_t b = begin; b < end; b += s->photon_cap) {
-        L.photon_begin = b;
-        L.n_photons = (int)std::min<int64_t>(s->photon_cap, end - b);
-        TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->stream));
-    TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), c->stream)); c->work_slot = 0;
-        k_photon_generate<<<g_stream, 256, 0, c->stream>>>(L);
-        c->stats.kernel_launches++;
-        for (int level = 1; level <= L.max_depth; ++level) {
-            const int cur = (level - 1) & 1;
-            launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap, L.hits,
-                          st + ST_NODES, ic + IC_ERROR);
-            k_photon_shade<<<occupancy_grid(c, k_photon_shade, 128), 128, 0, c->stream>>>(L, level);
-            c->stats.kernel_launches++;
+    if (begin < 0 || end > s->L.photons_per_iteration || begin > end) return c->fail("trace_sppm_photon_pass: bad photon range");
+    s->L.iteration = iteration;
+    const int64_t chunk = (int64_t)s->photon_cap * s->Kp;
+    for (int64_t b0 = begin;; b0 += chunk) {
+        const int64_t e0 = std::min(end, b0 + chunk);
+        if (!(s->traced_it == iteration && s->traced_begin == b0 && s->traced_end == e0))
+            if (trace_sppm_trace_photons(c, iteration, b0, e0)) return 1;
+        s->traced_it = -1;
+        // the deposits need the grid (main stream): every photon lane waits for it, deposits, and joins the main stream
+        TR_CUDA(c, cudaEventRecord(s->ev_grid, c->stream));
+        for (int j = 0; j < s->Kp; ++j) {
+            const int lane = s->Kc + j;
+            TR_CUDA(c, cudaStreamWaitEvent(c->side[lane], s->ev_grid, 0));
+            LaneScope scope(c, lane, c->side[lane]);
+            if (sppm_deposit_lane(c, s, j)) return 1;
+            TR_CUDA(c, cudaEventRecord(c->ev_join[lane], c->side[lane]));
+            TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[lane], 0));
         }
-        // deposit requests of all bounce levels in one launch (deposits do not feed back into the photon paths)
-        k_photon_deposit<<<occupancy_grid(c, k_photon_deposit, 128), 128, 0, c->stream>>>(L, 0);
-        c->stats.kernel_launches++;
-        k_sppm_stats<<<1, 32, 0, c->stream>>>(ic, st, L.max_depth, L.cap, 0);
-        c->stats.kernel_launches++;
+        if (e0 >= end) break;
     }
     TR_CUDA(c, cudaGetLastError());
     return 0;
@@ -765,7 +888,9 @@ extern "C" int trace_render_sppm(trace_ctx* c, const trace_camera* cam, const tr
     if (c->world != 1) { sppm_free(c); return c->fail("trace_render_sppm is single-GPU; use the stepwise trace_sppm_* API to shard photons"); }
     TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     for (int it = 1; it <= n_iterations; ++it) {
-        if (trace_sppm_camera_pass(c, it) || trace_sppm_photon_pass(c, it, 0, P) || trace_sppm_update(c)) { sppm_free(c); return 1; }
+        // photon tracing first: it is asynchronous and overlaps the camera pass (whose grid build ends with a host check)
+        if (trace_sppm_trace_photons(c, it, 0, P) || trace_sppm_camera_pass(c, it) || trace_sppm_photon_pass(c, it, 0, P) ||
+            trace_sppm_update(c)) { sppm_free(c); return 1; }
         if (on_image && write_frequency > 0 && (it % write_frequency == 0) && it != n_iterations) {   // sppm.jl:167-171
             if (trace_sppm_image(c, it, rgb_out)) { sppm_free(c); return 1; }
             on_image(user, it, rgb_out);

@@ -15,12 +15,17 @@
 #include "shading.cuh"
 #include "wavefront.cuh"
 
+// what may change between two renders that replay the same CUDA graph: read through a pointer, not baked into a node
+struct WhittedFrame {
+    DeviceCamera cam;
+    uint64_t seed;
+};
+
 struct WhittedLaunch {
     DeviceScene sc;
-    DeviceCamera cam;
+    const WhittedFrame* frame;
     DeviceFilm film;
     int spp, max_depth;
-    uint64_t seed;
     long long slot_begin;      // first slot of this batch (global over the rank's tile list)
     int n_slots;
     const int* tiles;          // tile indices owned by this rank
@@ -47,18 +52,20 @@ __device__ __forceinline__ void slot_to_pixel(const WhittedLaunch& L, long long 
 }
 
 __global__ void __launch_bounds__(256) k_wh_generate(WhittedLaunch L) {
+    const DeviceCamera cam = L.frame->cam;
+    const uint64_t seed = L.frame->seed;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.n_slots; i += gridDim.x * blockDim.x) {
         int px, py, s, tile;
         slot_to_pixel(L, L.slot_begin + i, px, py, s, tile);
         L.accum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (px > L.film.sb_x1 || py > L.film.sb_y1) { L.filmpos[i] = make_float2(-1e30f, -1e30f); continue; }
         const uint32_t pix = (uint32_t)((py - L.film.sb_y0) * (L.film.sb_x1 - L.film.sb_x0 + 1) + (px - L.film.sb_x0));
-        const float u0 = rng_uniform(L.seed, pix, (uint32_t)s, 0), u1 = rng_uniform(L.seed, pix, (uint32_t)s, 1);
+        const float u0 = rng_uniform(seed, pix, (uint32_t)s, 0), u1 = rng_uniform(seed, pix, (uint32_t)s, 1);
         const float fx = (float)px + u0, fy = (float)py + u1;
         float l0 = 0.0f, l1 = 0.0f;
-        if (L.cam.lens_radius > 0.0f) { l0 = rng_uniform(L.seed, pix, (uint32_t)s, 2); l1 = rng_uniform(L.seed, pix, (uint32_t)s, 3); }
+        if (cam.lens_radius > 0.0f) { l0 = rng_uniform(seed, pix, (uint32_t)s, 2); l1 = rng_uniform(seed, pix, (uint32_t)s, 3); }
         float3 o, d;
-        generate_camera_ray(L.cam, fx, fy, l0, l1, o, d);
+        generate_camera_ray(cam, fx, fy, l0, l1, o, d);
         L.filmpos[i] = make_float2(fx, fy);
         const int q = queue_claim(&L.counters[1]);
         L.ro[0][q] = f4(o, TR_INF);
@@ -234,18 +241,21 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     if (c->rank < 0 || c->rank >= c->world) return c->fail("rank %d outside world %d", c->rank, c->world);
     if (max_depth > 28) return c->fail("max_depth too large");
     WhittedLaunch L;
+    memset(&L, 0, sizeof(L));                                   // padding too: the struct's bytes key the graph cache
     L.sc = c->scene;
-    ctx_device_camera(cam, &L.cam);
+    WhittedFrame frame;
+    memset(&frame, 0, sizeof(frame));
+    ctx_device_camera(cam, &frame.cam);
+    frame.seed = seed;
+    TR_CUDA(c, c->b_misc[3].ensure(sizeof(WhittedFrame)));
+    TR_CUDA(c, cudaMemcpyAsync(c->b_misc[3].p, &frame, sizeof(frame), cudaMemcpyHostToDevice, c->stream));
+    L.frame = c->b_misc[3].as<WhittedFrame>();
     if (ctx_device_film(c, film, &L.film, &c->b_misc[0])) return 1;
-    L.spp = spp; L.max_depth = max_depth; L.seed = seed;
+    L.spp = spp; L.max_depth = max_depth;
     // this rank's tiles: k = rank, rank + world, ...   (16x16 sample tiles, sampler.jl:24-31)
     const int total_tiles = L.film.tiles_x * L.film.tiles_y;
     std::vector<int> tiles;
     for (int k = c->rank; k < total_tiles; k += c->world) tiles.push_back(k);
-    TR_CUDA(c, c->b_misc[1].ensure((tiles.size() + 1) * sizeof(int)));
-    if (!tiles.empty()) TR_CUDA(c, cudaMemcpyAsync(c->b_misc[1].p, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    TR_CUDA(c, cudaStreamSynchronize(c->stream));
-    L.tiles = c->b_misc[1].as<int>();
     const long long total_slots = (long long)tiles.size() * 256 * spp;
     // batches of (at most) c->batch samples, evened out.  Deep bounce levels hold few but expensive rays (a launch
     // cannot end before its slowest ray: ~0.2 ms for a 1000-node walk), so batches are large and up to `lanes` of them
@@ -259,6 +269,30 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     long long batch = (total_slots + nb - 1) / nb;
     batch = std::max<long long>(256, (batch + 255) / 256 * 256);
     nb = (total_slots + batch - 1) / batch;
+    {
+        // Batches are contiguous slot ranges, i.e. runs of the tile list.  In image order a run is a band of the image,
+        // and bands differ wildly in cost (sky vs. geometry): lanes with cheap bands drain at once and the expensive
+        // ones finish alone.  Deal groups of the rank's tiles (default: 2 tile rows - whole rows keep the BVH working set
+        // of a batch compact) to the batches round-robin instead, so every batch samples the whole image.  Measured on
+        // tess-1M: 1/8 of the frame 4.73 -> 4.53 ms, the full frame unchanged (profiles/r1_experiments.md).  The image
+        // does not depend on the order: the RNG is keyed by the pixel.
+        std::vector<int> dealt;
+        dealt.reserve(tiles.size());
+        const size_t G = c->deal > 0 ? (size_t)c->deal : std::max<size_t>(1, (size_t)(-c->deal) * L.film.tiles_x / c->world);
+        const size_t groups = (tiles.size() + G - 1) / G;
+        if (c->deal == 0) dealt = tiles;
+        else
+            for (long long j = 0; j < nb; ++j)
+                for (size_t g = (size_t)j; g < groups; g += (size_t)nb)
+                    for (size_t k = g * G; k < std::min(tiles.size(), (g + 1) * G); ++k) dealt.push_back(tiles[k]);
+        tiles.swap(dealt);
+    }
+    TR_CUDA(c, c->b_misc[1].ensure((tiles.size() + 1) * sizeof(int)));
+    if (!tiles.empty()) TR_CUDA(c, cudaMemcpyAsync(c->b_misc[1].p, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    L.tiles = c->b_misc[1].as<int>();
+    std::vector<long long> b_begin, b_count;
+    for (long long bi = 0; bi < nb; ++bi) { b_begin.push_back(bi * batch); b_count.push_back(std::min(batch, total_slots - bi * batch)); }
     const size_t cap_rays = (size_t)batch * (size_t)c->cap_percent / 100;
     const int shadow_mult = std::max(1, std::min(L.sc.n_lights, 4));
     const size_t cap_shadow = cap_rays * shadow_mult * 2;     // all bounce levels of a batch share one shadow queue
@@ -282,30 +316,64 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
         W.accum = c->b_queue[10].as<float4>() + (size_t)l * batch; W.filmpos = c->b_queue[11].as<float2>() + (size_t)l * batch;
         W.counters = ctx_icounters_lane(c, l);
     }
-    TR_CUDA(c, cudaMemsetAsync(L.film_rgbw, 0, npix * sizeof(float4), c->stream));
-    TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     TR_CUDA(c, c->b_misc[2].ensure((size_t)(nb + 1) * sizeof(int)));
     int* d_flags = c->b_misc[2].as<int>();
-    if (K > 1) {
-        TR_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
-        for (int l = 0; l < K; ++l) TR_CUDA(c, cudaStreamWaitEvent(c->side[l], c->ev_fork, 0));
-    }
-    int rc = 0;
-    for (long long bi = 0; bi < nb && !rc; ++bi) {
-        const int l = (int)(bi % K);
-        c->cur_lane = l;
-        c->cur_stream = K > 1 ? c->side[l] : c->stream;
-        const long long b = bi * batch;
-        rc = run_batch(c, lane[l], b, std::min(batch, total_slots - b), 0, d_flags + bi);
-    }
-    if (K > 1) {
-        for (int l = 0; l < K; ++l) {
-            cudaEventRecord(c->ev_join[l], c->side[l]);
-            cudaStreamWaitEvent(c->stream, c->ev_join[l], 0);
+    TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    // everything up to the lanes' join: film clear, then batch bi on lane bi % K
+    auto enqueue = [&]() -> int {
+        TR_CUDA(c, cudaMemsetAsync(L.film_rgbw, 0, npix * sizeof(float4), c->stream));
+        if (K > 1) {
+            TR_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+            for (int l = 0; l < K; ++l) TR_CUDA(c, cudaStreamWaitEvent(c->side[l], c->ev_fork, 0));
         }
+        int rc = 0;
+        for (long long bi = 0; bi < nb && !rc; ++bi) {
+            const int l = (int)(bi % K);
+            c->cur_lane = l;
+            c->cur_stream = K > 1 ? c->side[l] : c->stream;
+            rc = run_batch(c, lane[l], b_begin[bi], b_count[bi], 0, d_flags + bi);
+        }
+        if (K > 1) {
+            for (int l = 0; l < K; ++l) {
+                cudaEventRecord(c->ev_join[l], c->side[l]);
+                cudaStreamWaitEvent(c->stream, c->ev_join[l], 0);
+            }
+        }
+        c->cur_lane = 0;
+        c->cur_stream = c->stream;
+        return rc;
+    };
+    int rc = 0;
+    if (c->graph && !c->time_kernels && (size_t)c->stream > 2) {       // (legacy / per-thread default streams cannot be captured)
+        std::string key((const char*)lane.data(), lane.size() * sizeof(WhittedLaunch));
+        key.append((const char*)b_count.data(), b_count.size() * sizeof(long long));
+        const long long extra[] = {nb, batch, K, total_slots, (long long)(size_t)d_flags, c->slab, c->persist, c->count_nodes,
+                                   (long long)(size_t)c->stream};
+        key.append((const char*)extra, sizeof(extra));
+        if (!c->wh_graph || key != c->wh_graph_key) {
+            if (c->wh_graph) { cudaGraphExecDestroy(c->wh_graph); c->wh_graph = nullptr; }
+            const unsigned long long before = c->stats.kernel_launches;
+            TR_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+            rc = enqueue();
+            cudaGraph_t g = nullptr;
+            const cudaError_t e_end = cudaStreamEndCapture(c->stream, &g);
+            c->wh_graph_launches[0] = c->stats.kernel_launches - before;
+            c->stats.kernel_launches = before;
+            if (rc || e_end != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                return rc ? 1 : c->fail("CUDA graph capture of the render failed: %s", cudaGetErrorString(e_end));
+            }
+            const cudaError_t e_inst = cudaGraphInstantiate(&c->wh_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e_inst != cudaSuccess) { c->wh_graph = nullptr; return c->fail("cudaGraphInstantiate: %s", cudaGetErrorString(e_inst)); }
+            c->wh_graph_key = key;
+        }
+        TR_CUDA(c, cudaGraphLaunch(c->wh_graph, c->stream));
+        c->stats.kernel_launches += c->wh_graph_launches[0];
+    } else {
+        rc = enqueue();
     }
-    c->cur_lane = 0;
-    c->cur_stream = c->stream;
     if (rc) return 1;
     {
         std::vector<int> h_flags((size_t)nb + 2, 0), h_err((size_t)K, 0);
@@ -323,7 +391,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
         for (long long bi = 0; bi < nb; ++bi) {
             if (!h_flags[bi]) continue;                     // overflowed batches were not splatted: redo them in halves
             c->stats.queue_overflows++;
-            const long long b = bi * batch, cnt = std::min(batch, total_slots - b), half = cnt / 2;
+            const long long b = b_begin[bi], cnt = b_count[bi], half = cnt / 2;
             if (cnt < 2048) return c->fail("ray queue overflow that halving the batch cannot resolve");
             if (run_batch(c, lane[0], b, half, 1) || run_batch(c, lane[0], b + half, cnt - half, 1)) return 1;
         }

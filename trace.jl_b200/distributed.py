@@ -43,6 +43,31 @@ class _DevicePtr:
         self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
+def shares_torch_stream(ctx):
+    """True when the context enqueues on torch's current stream, so torch / NCCL work orders against it by itself."""
+    import torch
+    return bool(ctx.stream_handle) and ctx.stream_handle == torch.cuda.current_stream().cuda_stream
+
+
+class _Fence:
+    """Orders a block of torch work (collectives) against the context's stream.  Nothing to do when both use the same
+    stream; otherwise the context's stream is drained before and torch's current stream after."""
+
+    def __init__(self, ctx):
+        self.ctx, self.shared = ctx, shares_torch_stream(ctx)
+
+    def __enter__(self):
+        if not self.shared:
+            self.ctx.synchronize()
+        return self
+
+    def __exit__(self, *exc):
+        if not self.shared:
+            import torch
+            torch.cuda.current_stream().synchronize()
+        return False
+
+
 def allreduce_sum(tensor, group=None):
     """all_reduce(sum) when a process group exists; identity otherwise.  Backend-agnostic (nccl on GPUs, gloo in tests)."""
     import torch.distributed as dist
@@ -63,7 +88,8 @@ def render_whitted_sharded(ctx, scene, camera, spp, max_depth, seed, film_tensor
     ctx.check(ctx.lib.trace_render_whitted_device(ctx.h, C.byref(cam), C.byref(fd), int(spp), int(max_depth),
                                                   C.c_uint64(seed), C.c_void_p(film_tensor.data_ptr())))
     if reduce and world > 1:
-        dist.reduce(film_tensor, dst=0, op=dist.ReduceOp.SUM, group=group)
+        with _Fence(ctx):
+            dist.reduce(film_tensor, dst=0, op=dist.ReduceOp.SUM, group=group)
     return film_tensor
 
 
@@ -105,20 +131,24 @@ class SPPMSession:
         """One SPPM iteration (sppm.jl:153-165) over all ranks."""
         self.iteration += 1
         ctx = self.ctx
+        b, e = photon_range(self.photons, self.rank, self.world)
+        ctx.check(ctx.lib.trace_sppm_trace_photons(ctx.h, self.iteration, b, e))     # asynchronous: overlaps what follows
         ctx.check(ctx.lib.trace_sppm_camera_pass(ctx.h, self.iteration))
         if self.world > 1:
-            for which in range(2, 7):
-                self._all_gather(which)
+            with _Fence(ctx):
+                for which in range(2, 7):
+                    self._all_gather(which)
             ctx.check(ctx.lib.trace_sppm_build_grid(ctx.h))
-        b, e = photon_range(self.photons, self.rank, self.world)
         ctx.check(ctx.lib.trace_sppm_photon_pass(ctx.h, self.iteration, b, e))
         if self.world > 1:
-            allreduce_sum(self.buffers[0], self.group)
+            with _Fence(ctx):
+                allreduce_sum(self.buffers[0], self.group)
         ctx.check(ctx.lib.trace_sppm_update(ctx.h))
 
     def image(self):
         if self.world > 1:
-            self._all_gather(1)             # Ld is accumulated only by the rank that owns the row
+            with _Fence(self.ctx):
+                self._all_gather(1)         # Ld is accumulated only by the rank that owns the row
         h, w = self.camera.film.pixels.shape[:2]
         rgb = np.zeros((h, w, 3), dtype=np.float32)
         self.ctx.check(self.ctx.lib.trace_sppm_image(self.ctx.h, max(1, self.iteration), _lib.ptr(rgb)))

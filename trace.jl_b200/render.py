@@ -160,11 +160,14 @@ class UniformSampler:
 
 # ------------------------------------------------------------------ device context
 class Context:
-    """One trace_ctx (one GPU).  `stream` may be a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+    """One trace_ctx (one GPU).  `stream` may be a raw cudaStream_t of a NON-default stream (e.g. a torch.cuda.Stream's
+    .cuda_stream); with None / 0 (torch's default stream has handle 0) the library creates its own non-blocking stream,
+    which does not order against torch's work - `distributed.py` then fences with host synchronisation."""
 
     def __init__(self, device=0, stream=None):
         self.lib = _lib.load()
         self.h = C.c_void_p()
+        self.stream_handle = int(stream) if stream else 0
         rc = self.lib.trace_create(C.byref(self.h), int(device), C.c_void_p(stream) if stream else None)
         if rc != 0:
             raise RuntimeError(f"trace_create failed ({rc}): no usable CUDA device; there is no CPU fallback")
