@@ -13,6 +13,7 @@ torch.cuda.set_device(0)
 _s = torch.cuda.Stream(device=0)
 torch.cuda.set_stream(_s)
 ctx = T.Context(0, stream=_s.cuda_stream)
+ctx.set_option("persist", int(os.environ.get("PERSIST", "0")))
 ctx.set_option("sppm_lanes", int(os.environ.get("SPPM_LANES", "0")))
 sess = D.SPPMSession(ctx, scene, camera, kw["initial_search_radius"], kw["max_depth"], kw.get("photons_per_iteration", -1))
 for _ in range(2):
@@ -27,8 +28,17 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 st = ctx.stats()
-print(f"{name} sppm_lanes={os.environ.get('SPPM_LANES', '0')}: {iters / ms * 1e3:.2f} it/s  ({ms / iters:.3f} ms/it)  rays/it extend {st['rays_extend'] / iters:.0f} shadow {st['rays_shadow'] / iters:.0f} "
+print(f"{name} sppm_lanes={os.environ.get('SPPM_LANES', '0')} persist={os.environ.get('PERSIST', '0')}: {iters / ms * 1e3:.2f} it/s  ({ms / iters:.3f} ms/it)  rays/it extend {st['rays_extend'] / iters:.0f} shadow {st['rays_shadow'] / iters:.0f} "
       f"deposits/it {st['sppm_deposits'] / iters:.0f} launches/it {st['kernel_launches'] / iters:.1f} photons/it {sess.photons}")
+if os.environ.get("COUNT_NODES"):
+    ctx.set_option("count_nodes", 1)
+    ctx.reset_stats()
+    sess.step()
+    ctx.synchronize()
+    st = ctx.stats()
+    nr = st["rays_extend"] + st["rays_shadow"]
+    print(f"nodes/ray {st['nodes_visited'] / nr:.1f}  prims/ray {st['prims_tested'] / nr:.2f}  rays {nr}  prims_tested {st['prims_tested']}")
+    ctx.set_option("count_nodes", 0)
 img = sess.image()
 print("image mean", float(img.mean()), "max", float(img.max()))
 sess.close()

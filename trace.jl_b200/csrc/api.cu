@@ -9,7 +9,7 @@
 // One thread per ray, persistent grid-stride loop (grid = multiple of the SM count).  Rays come as two float4 arrays
 // {o.xyz, t_max} and {d.xyz, -}; the closest-hit result is one float4 {t, original+1 (bits), b0, b1}.
 template <int SLAB, bool COUNT>
-__global__ void __launch_bounds__(128) k_intersect(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
+__global__ void __launch_bounds__(128, 8) k_intersect(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
                                                    long long n, float4* __restrict__ hits, unsigned long long* counters,
                                                    int* error_flag) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128) k_intersect(DeviceScene sc, const float4*
     }
 }
 template <int SLAB, bool COUNT>
-__global__ void __launch_bounds__(128) k_occluded(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
+__global__ void __launch_bounds__(128, 8) k_occluded(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
                                                   long long n, uint8_t* __restrict__ out, unsigned long long* counters,
                                                   int* error_flag) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {

@@ -94,16 +94,17 @@ struct trace_ctx {
         kev_used++;
     }
     void kev_collect() {      // call after the stream has been synchronised
-        // debugging aid: TRACE_CUDA_TIMELINE=<file> appends "lane kind start_ms end_ms" (relative to the render's start
-        // event) for every timed traversal launch - a poor man's timeline of how the lanes overlap
+        // debugging aid: TRACE_CUDA_TIMELINE=<file> appends "lane kind start_ms end_ms" (relative to the first
+        // timed launch) for every timed traversal launch - a poor man's timeline of how the lanes overlap
         const char* tl_path = getenv("TRACE_CUDA_TIMELINE");
         FILE* tl = (tl_path && kev_used) ? fopen(tl_path, "a") : nullptr;
         if (tl) fprintf(tl, "# render\n");
         for (size_t i = 0; i < kev_used; ++i) {
             float ms = 0.0f;
+            cudaEventSynchronize(kev[i].b);                 // (launches on side streams may still be running)
             if (tl) {
                 float t0 = 0.0f, t1 = 0.0f;
-                if (cudaEventElapsedTime(&t0, ev0, kev[i].a) == cudaSuccess && cudaEventElapsedTime(&t1, ev0, kev[i].b) == cudaSuccess)
+                if (cudaEventElapsedTime(&t0, kev[0].a, kev[i].a) == cudaSuccess && cudaEventElapsedTime(&t1, kev[0].a, kev[i].b) == cudaSuccess)
                     fprintf(tl, "%d %d %.4f %.4f\n", kev[i].lane, kev[i].kind, t0, t1);
             }
             if (cudaEventElapsedTime(&ms, kev[i].a, kev[i].b) == cudaSuccess) {

@@ -191,7 +191,8 @@ struct HitRecord {
 // accepted closest hit shrinks t_max; interior -> near child next (sign of d[split_axis]), far child pushed untested.
 // Measured and rejected on B200 (profiles/r1_experiments.md): box-testing both children at their parent (0.7x), a
 // min/max reformulation of the slab test with fewer instructions (0.75-0.98x), persistent warps with dynamic ray
-// fetch (0.85x, kept below as option "persist").
+// fetch (0.85x, kept below as option "persist"), a "while-while" loop whose lanes meet before testing primitives (0.32x:
+// lanes standing on a leaf wait for the longest box-test walk of the warp), prefetching the pushed far child (0.98x).
 template <int SLAB, bool ANY, bool COUNT>
 __device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3 d, float tmax, HitRecord& out,
                                          unsigned long long* counters, int* error_flag) {
@@ -250,7 +251,11 @@ __device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3
         }
     }
 done:
+#ifdef TR_DEBUG_MAXNODES      // debugging aid: prims_tested becomes the LARGEST node count of any ray
+    if (COUNT && counters) { atomicAdd(&counters[0], (unsigned long long)n_nodes); atomicMax(&counters[1], (unsigned long long)n_nodes); }
+#else
     if (COUNT && counters) { atomicAdd(&counters[0], (unsigned long long)n_nodes); atomicAdd(&counters[1], (unsigned long long)n_prims); }
+#endif
     return found;
 }
 

@@ -6,8 +6,14 @@
 #include "context.hpp"
 #include "shading.cuh"
 
+// Traversal kernels are bound by dependent-fetch latency, so resident warps matter more than registers: capping them
+// at 64 registers (8 CTAs of 128 threads per SM instead of 7 at 69 registers; 20 B of spills) measured +12 % on tess-1M;
+// 9 CTAs (56 registers) +9 %, 10 CTAs (48 registers, 76 B spills) +4 % (profiles/r1_experiments.md).
+#ifndef TR_TRAV_MIN_BLOCKS
+#define TR_TRAV_MIN_BLOCKS 8
+#endif
 template <int SLAB, bool COUNT>
-__global__ void __launch_bounds__(128) k_wh_extend(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
+__global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_extend(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
                                                    const int* __restrict__ count, int cap, float4* __restrict__ hits,
                                                    unsigned long long* counters, int* error_flag) {
     const int n = min(*count, cap);
@@ -21,7 +27,7 @@ __global__ void __launch_bounds__(128) k_wh_extend(DeviceScene sc, const float4*
 }
 
 template <int SLAB, bool COUNT>
-__global__ void __launch_bounds__(128) k_wh_shadow(DeviceScene sc, const float4* __restrict__ so, const float4* __restrict__ sd,
+__global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_shadow(DeviceScene sc, const float4* __restrict__ so, const float4* __restrict__ sd,
                                                    const float4* __restrict__ contrib, const int* __restrict__ count, int cap,
                                                    float4* __restrict__ accum, unsigned long long* counters, int* error_flag) {
     const int n = min(*count, cap);
