@@ -61,7 +61,9 @@ struct trace_ctx {
     int deal = -2;                // groups of tiles dealt round-robin to the batches: g > 0 tiles, -r: r tile rows, 0: contiguous bands
     cudaGraphExec_t wh_graph = nullptr;
     std::string wh_graph_key;
-    unsigned long long wh_graph_launches[3] = {0, 0, 0};   // kernel / extend / shadow launches one replay stands for
+    unsigned long long wh_graph_launches[3] = {0, 0, 0};
+    std::vector<int> wh_tiles;              // the tile list currently in b_misc[1] (uploaded again only when it changes)
+    void* wh_tiles_dev = nullptr;   // kernel / extend / shadow launches one replay stands for
 
     // scene
     bool have_scene = false;

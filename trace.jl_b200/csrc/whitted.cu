@@ -164,7 +164,10 @@ __global__ void __launch_bounds__(256) k_wh_splat(WhittedLaunch L) {
 }
 
 // merge into the caller's film: xyz += to_XYZ(contrib), weight += w (film.jl:182-193)
-__global__ void k_film_finalize(const float4* __restrict__ rgbw, float4* __restrict__ film, int n) {
+// `skip` (device flag, may be null): set when a batch of this render overflowed a queue or a traversal failed - the host
+// then repairs the render and finalizes again, unconditionally.
+__global__ void k_film_finalize(const float4* __restrict__ rgbw, float4* __restrict__ film, int n, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 c = rgbw[i];
         float4 f = film[i];
@@ -174,6 +177,14 @@ __global__ void k_film_finalize(const float4* __restrict__ rgbw, float4* __restr
         f.w += c.w;
         film[i] = f;
     }
+}
+
+// any[0] = 1 when one of the render's batches overflowed or a traversal ran out of stack
+__global__ void k_wh_any_flag(const int* __restrict__ batch_flags, int n, const int* __restrict__ error_flag, int* __restrict__ any) {
+    int bad = 0;
+    for (int i = threadIdx.x; i < n; i += 32) bad |= batch_flags[i];
+    bad = __any_sync(0xffffffffu, bad != 0);
+    if (threadIdx.x == 0) *any = (bad || *error_flag) ? 1 : 0;
 }
 
 __global__ void k_wh_batch_stats(int* counters, unsigned long long* stats, int max_depth, int cap_rays, int cap_shadow,
@@ -206,24 +217,25 @@ static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long 
     for (int level = 1; level <= L.max_depth; ++level) {
         const int cur = (level - 1) & 1;
         launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap_rays,
-                      L.hits, st + ST_NODES, ic + IC_ERROR);
+                      L.hits, st + ST_NODES, ctx_icounters_lane(c, 0) + IC_ERROR);
         k_wh_shade<<<occupancy_grid(c, k_wh_shade, 128), 128, 0, c->cur_stream>>>(L, level);
         c->stats.kernel_launches++;
     }
     // one any-hit launch over the shadow rays of ALL bounce levels of the batch (they only feed the accumulators): a
     // single wide launch instead of max_depth launches that each wait for their slowest ray
     launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
-                  (const int*)(ic + 32), L.cap_shadow, L.accum, st + ST_NODES, ic + IC_ERROR);
+                  (const int*)(ic + 32), L.cap_shadow, L.accum, st + ST_NODES, ctx_icounters_lane(c, 0) + IC_ERROR);
     k_wh_splat<<<g_stream, 256, 0, c->cur_stream>>>(L);
     k_wh_batch_stats<<<1, 32, 0, c->cur_stream>>>(ic, st, L.max_depth, L.cap_rays, L.cap_shadow, batch_flag);
     c->stats.kernel_launches += 2;
     TR_CUDA(c, cudaGetLastError());
     if (batch_flag) return 0;
-    TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ic + IC_OVERFLOW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->cur_stream));
+    TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ic + IC_OVERFLOW, sizeof(int), cudaMemcpyDeviceToHost, c->cur_stream));
+    TR_CUDA(c, cudaMemcpyAsync(c->h_flags + 1, ctx_icounters_lane(c, 0) + IC_ERROR, sizeof(int), cudaMemcpyDeviceToHost, c->cur_stream));
     TR_CUDA(c, cudaStreamSynchronize(c->cur_stream));
     c->kev_collect();
     if (c->h_flags[1]) {
-        cudaMemsetAsync(ic + IC_ERROR, 0, sizeof(int), c->cur_stream);
+        cudaMemsetAsync(ctx_icounters_lane(c, 0) + IC_ERROR, 0, sizeof(int), c->cur_stream);
         return c->fail("traversal stack overflow (more than 64 pending nodes; the reference would throw a BoundsError, bvh.jl:222)");
     }
     if (c->h_flags[0]) {                                  // a queue overflowed: nothing was splatted, redo in halves
@@ -288,8 +300,11 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
         tiles.swap(dealt);
     }
     TR_CUDA(c, c->b_misc[1].ensure((tiles.size() + 1) * sizeof(int)));
-    if (!tiles.empty()) TR_CUDA(c, cudaMemcpyAsync(c->b_misc[1].p, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->wh_tiles_dev != c->b_misc[1].p || c->wh_tiles != tiles) {        // (re-rendering the same film: already there)
+        if (!tiles.empty()) TR_CUDA(c, cudaMemcpyAsync(c->b_misc[1].p, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        TR_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->wh_tiles = tiles; c->wh_tiles_dev = c->b_misc[1].p;
+    }
     L.tiles = c->b_misc[1].as<int>();
     std::vector<long long> b_begin, b_count;
     for (long long bi = 0; bi < nb; ++bi) { b_begin.push_back(bi * batch); b_count.push_back(std::min(batch, total_slots - bi * batch)); }
@@ -375,19 +390,22 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
         rc = enqueue();
     }
     if (rc) return 1;
-    {
-        std::vector<int> h_flags((size_t)nb + 2, 0), h_err((size_t)K, 0);
-        TR_CUDA(c, cudaMemcpyAsync(h_flags.data(), d_flags, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        for (int l = 0; l < K; ++l)
-            TR_CUDA(c, cudaMemcpyAsync(&h_err[l], ctx_icounters_lane(c, l) + IC_ERROR, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        TR_CUDA(c, cudaStreamSynchronize(c->stream));
-        c->kev_collect();
-        for (int l = 0; l < K; ++l) {
-            if (h_err[l]) {
-                cudaMemsetAsync(ctx_icounters_lane(c, l) + IC_ERROR, 0, sizeof(int), c->stream);
-                return c->fail("traversal stack overflow (more than 64 pending nodes; the reference would throw a BoundsError, bvh.jl:222)");
-            }
-        }
+    // optimistic tail: fold the flags, merge the film unless something went wrong, read the flags back - ONE host wait
+    int* d_err = ctx_icounters_lane(c, 0) + IC_ERROR;
+    k_wh_any_flag<<<1, 32, 0, c->stream>>>(d_flags, (int)nb, d_err, d_flags + nb);
+    k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix, d_flags + nb);
+    c->stats.kernel_launches += 2;
+    TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    std::vector<int> h_flags((size_t)nb + 2, 0);
+    TR_CUDA(c, cudaMemcpyAsync(h_flags.data(), d_flags, (size_t)(nb + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(c, cudaMemcpyAsync(&h_flags[(size_t)nb + 1], d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->kev_collect();
+    if (h_flags[(size_t)nb + 1]) {
+        cudaMemsetAsync(d_err, 0, sizeof(int), c->stream);
+        return c->fail("traversal stack overflow (more than 64 pending nodes; the reference would throw a BoundsError, bvh.jl:222)");
+    }
+    if (h_flags[(size_t)nb]) {
         for (long long bi = 0; bi < nb; ++bi) {
             if (!h_flags[bi]) continue;                     // overflowed batches were not splatted: redo them in halves
             c->stats.queue_overflows++;
@@ -395,11 +413,11 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
             if (cnt < 2048) return c->fail("ray queue overflow that halving the batch cannot resolve");
             if (run_batch(c, lane[0], b, half, 1) || run_batch(c, lane[0], b + half, cnt - half, 1)) return 1;
         }
+        k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix, nullptr);
+        c->stats.kernel_launches++;
+        TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+        TR_CUDA(c, cudaStreamSynchronize(c->stream));
     }
-    k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix);
-    c->stats.kernel_launches++;
-    TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    TR_CUDA(c, cudaStreamSynchronize(c->stream));
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->stats.ms_total = ms;
