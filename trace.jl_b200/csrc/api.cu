@@ -55,6 +55,8 @@ extern "C" int trace_create(trace_ctx** out, int device, void* cuda_stream) {
     ok = ok && c->b_counters.ensure(ctx_counter_bytes()) == cudaSuccess;
     c->cur_stream = c->stream;
     ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int l = 0; l < trace_ctx::MAX_LANES && ok; ++l)
         ok = cudaStreamCreateWithFlags(&c->side[l], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming) == cudaSuccess;
@@ -79,6 +81,8 @@ extern "C" void trace_destroy(trace_ctx* c) {
     for (auto& e : c->kev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int l = 0; l < trace_ctx::MAX_LANES; ++l) { if (c->side[l]) cudaStreamDestroy(c->side[l]); if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->wh_graph) cudaGraphExecDestroy(c->wh_graph);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -466,8 +470,15 @@ extern "C" int trace_render_whitted(trace_ctx* c, const trace_camera* cam, const
     const size_t w = (size_t)(film->crop_x1 - film->crop_x0 + 1), h = (size_t)(film->crop_y1 - film->crop_y0 + 1);
     const size_t bytes = w * h * 4 * sizeof(float);
     TR_CUDA(c, c->b_misc[7].ensure(bytes));
-    TR_CUDA(c, cudaMemcpyAsync(c->b_misc[7].p, film_xyzw, bytes, cudaMemcpyHostToDevice, c->stream));
-    if (trace_render_whitted_device(c, cam, film, spp, max_depth, seed, c->b_misc[7].p)) return 1;
+    // the caller's film is only needed by the final merge: upload it on the copy stream while the render runs
+    TR_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+    TR_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+    TR_CUDA(c, cudaMemcpyAsync(c->b_misc[7].p, film_xyzw, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    TR_CUDA(c, cudaEventRecord(c->ev_copy, c->copy_stream));
+    c->film_upload_pending = true;
+    const int rc = trace_render_whitted_device(c, cam, film, spp, max_depth, seed, c->b_misc[7].p);
+    if (c->film_upload_pending) { cudaStreamWaitEvent(c->stream, c->ev_copy, 0); c->film_upload_pending = false; }
+    if (rc) { cudaStreamSynchronize(c->stream); return 1; }
     TR_CUDA(c, cudaMemcpyAsync(film_xyzw, c->b_misc[7].p, bytes, cudaMemcpyDeviceToHost, c->stream));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;

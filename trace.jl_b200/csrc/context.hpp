@@ -38,6 +38,9 @@ struct trace_ctx {
     static const int MAX_LANES = 16;
     cudaStream_t side[MAX_LANES] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {};
+    cudaStream_t copy_stream = nullptr;     // host film upload of trace_render_whitted, overlapped with the render
+    cudaEvent_t ev_copy = nullptr;
+    bool film_upload_pending = false;       // the film merge must wait for ev_copy
     cudaStream_t cur_stream = nullptr;      // stream the launch helpers enqueue on (== stream outside a laned render)
     int cur_lane = 0;
     int lanes = 12;

@@ -393,6 +393,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     // optimistic tail: fold the flags, merge the film unless something went wrong, read the flags back - ONE host wait
     int* d_err = ctx_icounters_lane(c, 0) + IC_ERROR;
     k_wh_any_flag<<<1, 32, 0, c->stream>>>(d_flags, (int)nb, d_err, d_flags + nb);
+    if (c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
     k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix, d_flags + nb);
     c->stats.kernel_launches += 2;
     TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
