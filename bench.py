@@ -119,6 +119,19 @@ def build_scene(T, workload):
     return scene, camera, spp, depth
 
 
+def calibrate_tiles(osc, cam, fd, spp, depth, film, cores, total_tiles, target_s):
+    """Number of 16x16 tiles (strided over the image) the CPU restatement renders in about `target_s` seconds."""
+    tiles = min(total_tiles, max(cores * 4, 64))
+    for _ in range(5):
+        t0 = time.time()
+        osc.render_whitted(cam, fd, spp, depth, 1, film, max_tiles=tiles, threads=cores)
+        dt = time.time() - t0
+        if tiles >= total_tiles or dt >= 0.6 * target_s:
+            break
+        tiles = int(min(total_tiles, tiles * min(16.0, max(1.5, target_s / max(dt, 1e-3)))))
+    return tiles
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (the C++ restatement, oracle/ — Julia is
     not available) with all host threads, on a bounded sample (a strided subset of the 16x16 tiles) of the workload."""
@@ -135,10 +148,9 @@ def run_reference(args):
     film = np.zeros_like(camera.film.pixels)
     from trace_jl_b200.distributed import n_sample_tiles
     total_tiles = n_sample_tiles(camera.film)
-    # calibrate: ~4 s per step
-    t0 = time.time(); cnt = osc.render_whitted(cam, fd, spp, depth, 1, film, max_tiles=max(cores, 16), threads=cores); dt = time.time() - t0
-    rate = (int(cnt[0]) + int(cnt[1])) / max(dt, 1e-6)
-    tiles = int(min(total_tiles, max(cores, 16) * max(1.0, args.ref_seconds / max(dt, 1e-3))))
+    # bounded sample per step: ~ref_seconds of CPU work, and the whole run within ~2 minutes
+    target = min(args.ref_seconds, 120.0 / max(1, args.steps + args.warmup))
+    tiles = calibrate_tiles(osc, cam, fd, spp, depth, film, cores, total_tiles, target)
     times, rays = [], []
     for i in range(args.warmup + args.steps):
         film[:] = 0
@@ -384,9 +396,7 @@ def main():
         cores = os.cpu_count() or 1
         tmp = np.zeros_like(camera.film.pixels)
         total_tiles = D.n_sample_tiles(camera.film)
-        tiles = max(cores, 16)
-        t0 = time.time(); cnt = osc.render_whitted(cam_pod, fd, spp, depth, 1, tmp, max_tiles=tiles, threads=cores); dt = time.time() - t0
-        tiles2 = int(min(total_tiles, tiles * max(1.0, 12.0 / max(dt, 1e-3))))
+        tiles2 = calibrate_tiles(osc, cam_pod, fd, spp, depth, tmp, cores, total_tiles, 12.0)
         t0 = time.time(); cnt = osc.render_whitted(cam_pod, fd, spp, depth, 1, tmp, max_tiles=tiles2, threads=cores); dt = time.time() - t0
         cpu_baseline = {"value": (int(cnt[0]) + int(cnt[1])) / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                         "sample": f"{tiles2} of {total_tiles} 16x16 sample tiles (strided over the image), {spp} spp, depth {depth}, {dt:.1f} s",

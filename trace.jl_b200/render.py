@@ -71,9 +71,7 @@ class Film:
         d.crop_x0, d.crop_y0 = int(self.crop_bounds.p_min[0]), int(self.crop_bounds.p_min[1])
         d.crop_x1, d.crop_y1 = int(self.crop_bounds.p_max[0]), int(self.crop_bounds.p_max[1])
         d.filter_radius[0], d.filter_radius[1] = float(self.filter.radius[0]), float(self.filter.radius[1])
-        flat = self.filter_table.reshape(-1)
-        for i in range(256):
-            d.filter_table[i] = float(flat[i])
+        C.memmove(d.filter_table, np.ascontiguousarray(self.filter_table, dtype=np.float32).ctypes.data, 256 * 4)
         d.scale = float(self.scale)
         return d
 
