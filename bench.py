@@ -113,9 +113,9 @@ class ClockSampler:
                 "samples": len(self.sm), "source": "nvml, 5 ms period, during the timed region"}
 
 
-def build_scene(T, workload):
+def build_scene(T, workload, builder="reference"):
     kw, spp, depth = WORKLOADS[workload]
-    scene, camera, _ = T.scenes.tessellated(**kw)
+    scene, camera, _ = T.scenes.tessellated(**kw, builder=builder)
     return scene, camera, spp, depth
 
 
@@ -181,10 +181,13 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--persist", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=12)
+    ap.add_argument("--builder", default="reference", choices=["reference", "sah"],
+                    help="BVH build: the reference's split logic (default, bit-identical tree) or the opt-in conventional SAH")
     ap.add_argument("--graph", type=int, default=1, help="replay the render as one CUDA graph (0: direct launches)")
     ap.add_argument("--ref-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sppm", action="store_true")
+    ap.add_argument("--no-optin", action="store_true", help="skip the extra measurement on the opt-in SAH tree")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -214,7 +217,7 @@ def main():
     if args.batch:
         ctx.set_option("batch", args.batch)
 
-    scene, camera, spp, depth = build_scene(T, args.workload)
+    scene, camera, spp, depth = build_scene(T, args.workload, args.builder)
     flat = ctx.upload(scene)
     H, W = camera.film.pixels.shape[:2]
     film_dev = torch.zeros((H, W, 4), dtype=torch.float32, device=f"cuda:{local}")
@@ -365,26 +368,67 @@ def main():
     e2e = {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(film_bytes + C.sizeof(cam_pod) + C.sizeof(fd)),
            "d2h_bytes_per_step": int(film_bytes), "ms_per_step": float(ms2.item()) / args.steps}
 
-    # ---- secondary metric: SPPM iterations/s on docs/code/spheres.jl ("shadows", 1024^2, depth 5), photons sharded
-    sppm = None
-    if not args.no_sppm:
-        s_scene, s_cam, kw = T.scenes.shadows(resolution=1024)
-        sess = D.SPPMSession(ctx, s_scene, s_cam, kw["initial_search_radius"], kw["max_depth"], -1, 0x5EED0001, rank, world)
-        for _ in range(3):
-            sess.step()
+    # ---- the same workload on the OPT-IN tree: BVHAccel(..., builder="sah") - same hits (t bit-identical,
+    # primitives equal except ties of equal t: tests/test_gpu_parity.py::test_optin_sah_tree_on_gpu), fewer box tests.
+    # Reported next to the headline, which stays on the reference's own tree.
+    optin = None
+    if args.builder == "reference" and not args.no_optin:
+        scene2, camera2, _, _ = build_scene(T, args.workload, "sah")
+        ctx.upload(scene2)
+
+        def step2(i):
+            film_dev.zero_()
+            D.render_whitted_sharded(ctx, scene2, camera2, spp, depth, 3000 + i, film_dev, rank, world, reduce=False)
+            if world > 1:
+                dist.reduce(film_dev, dst=0, op=dist.ReduceOp.SUM)
+
+        for i in range(args.warmup):
+            step2(i)
         barrier()
-        n_it = 10
+        ctx.reset_stats()
+        barrier()
         e0.record()
-        for _ in range(n_it):
-            sess.step()
+        for i in range(args.steps):
+            step2(args.warmup + i)
         e1.record()
         barrier()
-        ms3 = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local}")
+        ms4 = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local}")
+        st4 = ctx.stats()
+        rays4 = torch.tensor([float(st4["rays_extend"] + st4["rays_shadow"])], device=f"cuda:{local}", dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
-        sppm = {"metric": "SPPM iterations/sec", "value": n_it / (float(ms3.item()) * 1e-3), "unit": "it/s",
-                "config": {"workload": "sppm-shadows-1024", "photons_per_iteration": sess.photons, "max_depth": kw["max_depth"]}}
-        sess.close()
+            dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+            dist.all_reduce(rays4, op=dist.ReduceOp.SUM)
+        optin = {"bvh_builder": "opt-in conventional binned SAH (trace_bvh_build_sah)", "value": float(rays4.item()) / (float(ms4.item()) * 1e-3) / 1e6,
+                 "unit": "Mrays/s", "ms_per_step": float(ms4.item()) / args.steps, "bvh_nodes": int(len(scene2.flatten().nodes))}
+        ctx.upload(scene)
+
+    # ---- secondary metric: SPPM iterations/s, photons sharded over the ranks (camera pass by image rows):
+    # configs[1] docs/code/spheres.jl ("shadows", 1024^2, depth 5) and configs[3] docs/code/caustic_moving.jl (one frame's
+    # scene, 1024^2, 1.25 M photons per iteration, depth 5)
+    sppm = None
+    if not args.no_sppm:
+        sppm = []
+        for name, make in (("sppm-shadows-1024", lambda: T.scenes.shadows(resolution=1024)),
+                           ("sppm-caustic-moving-1024", lambda: T.scenes.caustic_moving())):
+            s_scene, s_cam, kw = make()
+            sess = D.SPPMSession(ctx, s_scene, s_cam, kw["initial_search_radius"], kw["max_depth"],
+                                 kw.get("photons_per_iteration", -1), 0x5EED0001, rank, world)
+            for _ in range(3):
+                sess.step()
+            barrier()
+            n_it = 10
+            e0.record()
+            for _ in range(n_it):
+                sess.step()
+            e1.record()
+            barrier()
+            ms3 = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local}")
+            if world > 1:
+                dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+            sppm.append({"metric": "SPPM iterations/sec", "value": n_it / (float(ms3.item()) * 1e-3), "unit": "it/s",
+                         "config": {"workload": name, "photons_per_iteration": sess.photons, "max_depth": kw["max_depth"],
+                                    "primitives": int(s_scene.aggregate.n_primitives)}})
+            sess.close()
         ctx.upload(scene)
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample of the same workload
@@ -408,11 +452,14 @@ def main():
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"whitted-{args.workload}", "spp": spp, "max_depth": depth,
                           "resolution": list(WORKLOADS[args.workload][0]["res"]), "triangles": int(scene.aggregate.n_primitives),
-                          "bvh_nodes": int(len(flat.nodes)), "slab_test": {0: "literal (bounds.jl:180-200)", 1: "textbook (not hit-equivalent)", 2: "guarded (literal AND conservative interval; hit-identical, tests/test_gpu_parity.py)"}[args.slab],
+                          "bvh_nodes": int(len(flat.nodes)),
+                          "bvh_builder": {"reference": "reference split logic (src/accel/bvh.jl:87-185), bit-identical tree",
+                                          "sah": "opt-in conventional binned SAH (same hits, ties aside)"}[args.builder],
+                          "slab_test": {0: "literal (bounds.jl:180-200)", 1: "textbook (not hit-equivalent)", 2: "guarded (literal AND conservative interval; hit-identical, tests/test_gpu_parity.py)"}[args.slab],
                           "parallelism": f"tiles-rr{world}", "lanes": args.lanes, "l2_policy": "inputs larger than L2 (ray queues + BVH > 126 MB per step)",
                           "rays_per_step": total_rays / args.steps},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-               "sppm": sppm, "breakdown": breakdown}
+               "sppm": sppm, "optin_sah_tree": optin, "breakdown": breakdown}
         print(json.dumps(out))
     ctx.close()
     if world > 1:

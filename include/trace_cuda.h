@@ -138,6 +138,9 @@ typedef struct trace_bvh trace_bvh;
 /* ---- host-side BVH build, no GPU needed ---- */
 int     trace_bvh_build(const float* prim_bounds /* [n][6] = min xyz, max xyz */, int64_t n,
                         int max_node_primitives, trace_bvh** out);
+/* opt-in: conventional binned SAH (primitive-count weighted, empty buckets, leaves up to max_node_primitives) in the same
+ * node format.  Not the reference's tree: closest hits agree except for ties between equal t. */
+int     trace_bvh_build_sah(const float* prim_bounds, int64_t n, int max_node_primitives, trace_bvh** out);
 int64_t trace_bvh_num_nodes(const trace_bvh* bvh);
 int64_t trace_bvh_num_prims(const trace_bvh* bvh);
 int     trace_bvh_copy(const trace_bvh* bvh, trace_bvh_node* nodes_out, uint32_t* prim_order_out);

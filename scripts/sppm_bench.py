@@ -8,6 +8,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "shadows"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 res = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 kw_res = dict(resolution=res) if res else {}
+if os.environ.get("BUILDER"):
+    kw_res.update(builder=os.environ["BUILDER"], max_node_primitives=int(os.environ.get("MNP", "1")))
 scene, camera, kw = getattr(T.scenes, name)(**kw_res)
 torch.cuda.set_device(0)
 _s = torch.cuda.Stream(device=0)
@@ -28,7 +30,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 st = ctx.stats()
-print(f"{name} sppm_lanes={os.environ.get('SPPM_LANES', '0')} persist={os.environ.get('PERSIST', '0')}: {iters / ms * 1e3:.2f} it/s  ({ms / iters:.3f} ms/it)  rays/it extend {st['rays_extend'] / iters:.0f} shadow {st['rays_shadow'] / iters:.0f} "
+print(f"{name} builder={os.environ.get('BUILDER', 'reference')}/{os.environ.get('MNP', '1')} sppm_lanes={os.environ.get('SPPM_LANES', '0')} persist={os.environ.get('PERSIST', '0')}: {iters / ms * 1e3:.2f} it/s  ({ms / iters:.3f} ms/it)  rays/it extend {st['rays_extend'] / iters:.0f} shadow {st['rays_shadow'] / iters:.0f} "
       f"deposits/it {st['sppm_deposits'] / iters:.0f} launches/it {st['kernel_launches'] / iters:.1f} photons/it {sess.photons}")
 if os.environ.get("COUNT_NODES"):
     ctx.set_option("count_nodes", 1)

@@ -14,7 +14,8 @@ lanes_list = [int(a) for a in sys.argv[2:]] or [12, 6, 4, 2, 1]
 _s = torch.cuda.Stream(device=0)
 torch.cuda.set_stream(_s)
 ctx = T.Context(0, stream=_s.cuda_stream)
-scene, camera, spp, depth = bench.build_scene(T, "tess-1M")
+kw_b, spp, depth = bench.WORKLOADS["tess-1M"]
+scene, camera, _ = T.scenes.tessellated(**kw_b, builder=os.environ.get("BUILDER", "reference"), max_node_primitives=int(os.environ.get("MNP", "1")))
 spp = spp_override or spp
 depth = int(os.environ.get("DEPTH", depth))
 H, W = camera.film.pixels.shape[:2]
@@ -40,5 +41,5 @@ for graph in graphs:
         st = ctx.stats()
         ms = e0.elapsed_time(e1) / n
         rays = (st["rays_extend"] + st["rays_shadow"]) / n
-        print(f"depth {depth} spp {spp} world {world} graph {graph} lanes {lanes:2d}: {ms:7.3f} ms/render  {rays / ms / 1e3:8.1f} Mrays/s per rank  "
+        print(f"builder {os.environ.get('BUILDER', 'reference')}/{os.environ.get('MNP', '1')} depth {depth} spp {spp} world {world} graph {graph} lanes {lanes:2d}: {ms:7.3f} ms/render  {rays / ms / 1e3:8.1f} Mrays/s per rank  "
               f"launches/render {st['kernel_launches'] / n:.0f}  inner(ev0..ev1 of last render) {st['ms_total']:.3f} ms", flush=True)

@@ -457,3 +457,48 @@ def test_integrator_functors(T, ctx, tmp_path):
     scene, camera, kw = T.scenes.shadows(resolution=40, filename=str(tmp_path / "s.png"))
     img = T.SPPMIntegrator(camera, 0.05, 5, 2, -1, 2, context=ctx)(scene)
     assert img.shape == (40, 40, 3) and float(img.max()) > 0 and os.path.getsize(tmp_path / "s.png") > 100
+
+
+def test_optin_sah_tree_on_gpu(T, ctx):
+    """the opt-in conventional SAH tree (BVHAccel(..., builder="sah")).  On the GPU, over 2e6 rays of the
+    caustic mesh: t bit-identical to the reference tree's, the same primitive except on ties of equal t, fewer box
+    tests; the oracle walking the SAME sah tree agrees with the GPU bit for bit (prim, t, barycentrics); and a Whitted
+    image rendered on either tree is the same image."""
+    rng = np.random.default_rng(11)
+    n = 2_000_000
+    flats = {}
+    for builder in ("reference", "sah"):
+        scene, _, _ = T.scenes.caustic_glass(builder=builder)
+        flats[builder] = (scene, scene.flatten())
+    lo, hi = flats["reference"][1].nodes[0]["bmin"], flats["reference"][1].nodes[0]["bmax"]
+    target = (lo + rng.random((n, 3), dtype=np.float32) * (hi - lo)).astype(np.float32)
+    origin = np.where(rng.random((n, 1)) < 0.5, np.array([[0, 150, 150]], np.float32),
+                      (target + rng.normal(size=(n, 3)).astype(np.float32) * 20)).astype(np.float32)
+    d = (target - origin).astype(np.float32)
+    out = {}
+    for builder, (scene, flat) in flats.items():
+        ctx.upload(scene)
+        ctx.set_option("count_nodes", 1)
+        ctx.reset_stats()
+        out[builder] = ctx.intersect(origin, d) + (ctx.stats()["nodes_visited"],)
+        ctx.set_option("count_nodes", 0)
+    (pa, ta, ba, na), (pb, tb, bb, nb) = out["reference"], out["sah"]
+    assert (pa != 0).sum() > n // 4
+    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+    assert (pa != pb).mean() < 1e-3
+    assert nb < na
+    m = 100_000
+    op, ot, ob = oracle_lib.OracleScene(flats["sah"][1]).intersect(origin[:m], d[:m], slab=0)
+    assert np.array_equal(op, pb[:m]) and np.array_equal(ot.view(np.uint32), tb[:m].view(np.uint32))
+    assert np.array_equal(ob.view(np.uint32), bb[:m].view(np.uint32))
+    # images
+    films = []
+    for builder in ("reference", "sah"):
+        scene, camera, _ = T.scenes.tessellated(cells=48, stacks=26, slices=24, res=(160, 90), builder=builder)
+        ctx.upload(scene)
+        cam, fd = camera.pod(), camera.film.desc()
+        film = np.zeros_like(camera.film.pixels)
+        ctx.check(ctx.lib.trace_render_whitted(ctx.h, C.byref(cam), C.byref(fd), 4, 5, C.c_uint64(9), T._lib.ptr(film)))
+        films.append(film)
+    rel_mse, frac, werr = image_report(films[1], films[0], "whitted/tess-small sah-vs-reference tree")
+    assert werr < 1e-5 and rel_mse < 1e-5 and frac > 0.998

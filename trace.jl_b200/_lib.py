@@ -62,6 +62,7 @@ SPPM_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float))
 _P = C.c_void_p
 SIGNATURES = {
     "trace_bvh_build": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(_P)]),
+    "trace_bvh_build_sah": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(_P)]),
     "trace_bvh_num_nodes": (C.c_int64, [_P]),
     "trace_bvh_num_prims": (C.c_int64, [_P]),
     "trace_bvh_copy": (C.c_int, [_P, _P, _P]),

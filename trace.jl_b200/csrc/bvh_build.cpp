@@ -9,6 +9,7 @@
 // permutation that is partitioned in place, and nodes emitted directly in the flattened preorder (first child =
 // parent + 1), so building the 10 M-triangle scene needs no recursion and no per-node heap traffic.
 // Compiled with -ffp-contract=off: the cost arithmetic must round like the reference's.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -177,6 +178,125 @@ extern "C" int trace_bvh_build(const float* pb, int64_t n, int max_node_primitiv
             bvh->nodes.push_back(node);
             todo.push_back({mid + 1, t.to, slot});     // second child: patched into `offset` when it is emitted
             todo.push_back({t.from, mid, -1});          // first child: emitted next, at slot + 1
+        }
+    }
+    *out = bvh;
+    return 0;
+}
+
+// Opt-in alternative: a conventional binned SAH over the same inputs, emitted in the same node format,
+// so every kernel runs on it unchanged.  Differences from the literal build above: buckets start EMPTY, each side is
+// weighted by its primitive COUNT (cost = 1/8 + (nL*aL + nR*aR)/A), a node becomes a leaf when that is cheaper and it
+// holds <= max_node_primitives, the partition tests every element, and a degenerate split falls back to the median.
+// The closest hit of a ray does not depend on the tree (ties between equal t aside), so images agree; traversal work
+// drops because the literal cost function is degenerate (Q16: depth 42 and 2 663 empty leaves on the caustic mesh).
+extern "C" int trace_bvh_build_sah(const float* pb, int64_t n, int max_node_primitives, trace_bvh** out) {
+    if (!out || n < 0 || (n > 0 && !pb)) return 1;
+    *out = nullptr;
+    trace_bvh* bvh = new (std::nothrow) trace_bvh();
+    if (!bvh) return 2;
+    if (n == 0) { *out = bvh; return 0; }
+    const int max_prims = max_node_primitives < 1 ? 1 : (max_node_primitives < 255 ? max_node_primitives : 255);
+    const int NB = 16;
+    std::vector<float> cen((size_t)n * 3);
+    std::vector<uint32_t> perm((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        perm[i] = (uint32_t)i;
+        for (int k = 0; k < 3; ++k) cen[3 * i + k] = 0.5f * pb[6 * i + k] + 0.5f * pb[6 * i + 3 + k];
+    }
+    try {
+        bvh->nodes.reserve((size_t)(2 * n + 16));
+        bvh->order.reserve((size_t)n);
+    } catch (...) { delete bvh; return 2; }
+    std::vector<Task> todo;
+    todo.push_back({0, n - 1, -1});
+    while (!todo.empty()) {
+        const Task t = todo.back();
+        todo.pop_back();
+        const int64_t slot = (int64_t)bvh->nodes.size();
+        if (t.patch >= 0) bvh->nodes[t.patch].offset = (uint32_t)slot;
+        const int64_t count = t.to - t.from + 1;
+        Box all; all.reset();
+        Box cb; cb.reset();
+        for (int64_t i = t.from; i <= t.to; ++i) {
+            const float* b = pb + 6 * (size_t)perm[i];
+            all.grow(b, b + 3);
+            const float* c = &cen[3 * (size_t)perm[i]];
+            cb.grow(c, c);
+        }
+        trace_bvh_node node;
+        for (int k = 0; k < 3; ++k) { node.bmin[k] = all.lo[k]; node.bmax[k] = all.hi[k]; }
+        const int axis = cb.widest();
+        bool leaf = count == 1 || !cb.valid() || !(cb.hi[axis] > cb.lo[axis]);
+        if (leaf && count > max_prims && count > 1) leaf = false;        // identical centroids: split at the median
+        int64_t mid = (t.from + t.to) / 2;                                 // last index of the left side
+        if (!leaf) {
+            bool split_done = false;
+            if (cb.valid() && cb.hi[axis] > cb.lo[axis] && count >= 2) {
+                const float scale = (float)NB / (cb.hi[axis] - cb.lo[axis]);
+                auto bucket = [&](uint32_t prim) -> int {
+                    int b = (int)((cen[3 * (size_t)prim + axis] - cb.lo[axis]) * scale);
+                    return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                };
+                Box bk[NB];
+                int64_t cnt[NB];
+                for (int b = 0; b < NB; ++b) { bk[b].reset(); cnt[b] = 0; }
+                for (int64_t i = t.from; i <= t.to; ++i) {
+                    const uint32_t p = perm[i];
+                    const float* b = pb + 6 * (size_t)p;
+                    const int k = bucket(p);
+                    bk[k].grow(b, b + 3); cnt[k]++;
+                }
+                float right_area[NB];
+                int64_t right_cnt[NB];
+                Box acc; acc.reset();
+                int64_t c = 0;
+                for (int b = NB - 1; b >= 1; --b) {
+                    if (cnt[b]) acc.grow(bk[b]);
+                    c += cnt[b];
+                    right_area[b] = c ? acc.area() : 0.0f; right_cnt[b] = c;
+                }
+                acc.reset(); c = 0;
+                const float total_area = all.area();
+                float best_cost = kInf;
+                int best = -1;
+                for (int b = 0; b < NB - 1; ++b) {                          // split after bucket b
+                    if (cnt[b]) acc.grow(bk[b]);
+                    c += cnt[b];
+                    if (c == 0 || right_cnt[b + 1] == 0) continue;
+                    const float cost = 0.125f + ((float)c * acc.area() + (float)right_cnt[b + 1] * right_area[b + 1]) /
+                                                    (total_area > 0.0f ? total_area : 1.0f);
+                    if (cost < best_cost) { best_cost = cost; best = b; }
+                }
+                if (best >= 0 && (count > max_prims || best_cost < (float)count)) {
+                    int64_t left = t.from;
+                    for (int64_t i = t.from; i <= t.to; ++i)
+                        if (bucket(perm[i]) <= best) { std::swap(perm[i], perm[left]); ++left; }
+                    mid = left - 1;
+                    split_done = mid >= t.from && mid < t.to;
+                } else if (best >= 0 || count <= max_prims) {
+                    leaf = count <= max_prims;
+                }
+            }
+            if (!leaf && !split_done) {
+                // median split along the axis (also: two primitives, or all centroids in one bucket)
+                mid = (t.from + t.to) / 2;
+                std::nth_element(perm.begin() + t.from, perm.begin() + mid, perm.begin() + t.to + 1, [&](uint32_t a, uint32_t b) {
+                    return cen[3 * (size_t)a + axis] < cen[3 * (size_t)b + axis];
+                });
+            }
+        }
+        if (leaf) {
+            node.offset = (uint32_t)bvh->order.size();
+            node.meta = TRACE_NODE_LEAF | (uint32_t)count;
+            for (int64_t i = t.from; i <= t.to; ++i) bvh->order.push_back(perm[i]);
+            bvh->nodes.push_back(node);
+        } else {
+            node.offset = 0;
+            node.meta = (uint32_t)axis << 30;
+            bvh->nodes.push_back(node);
+            todo.push_back({mid + 1, t.to, slot});
+            todo.push_back({t.from, mid, -1});
         }
     }
     *out = bvh;

@@ -292,8 +292,13 @@ class BVHAccel:
     """BVHAccel(primitives, max_node_primitives = 1), src/accel/bvh.jl:50-80.  The build itself is
     trace_bvh_build in libtrace_cuda.so's host part (the reference's SAH split logic)."""
 
-    def __init__(self, primitives, max_node_primitives=1):
+    def __init__(self, primitives, max_node_primitives=1, builder="reference"):
+        """builder = "reference": the reference's split logic, bit-identical tree (src/accel/bvh.jl:55-206).
+        builder = "sah": opt-in conventional binned SAH (trace_bvh_build_sah) - same hits, ties aside; less traversal."""
         lib = _lib.load()
+        if builder not in ("reference", "sah"):
+            raise ValueError("builder must be 'reference' or 'sah'")
+        self.builder = builder
         self.max_node_primitives = min(255, int(max_node_primitives))
         self.items = _expand(primitives)
         # flat per-primitive table in the caller's order
@@ -318,7 +323,8 @@ class BVHAccel:
             return
         self.prim_bounds = np.ascontiguousarray(np.concatenate(bounds, axis=0), dtype=np.float32)
         h = C.c_void_p()
-        rc = lib.trace_bvh_build(_lib.ptr(self.prim_bounds), self.n_primitives, self.max_node_primitives, C.byref(h))
+        build = lib.trace_bvh_build if builder == "reference" else lib.trace_bvh_build_sah
+        rc = build(_lib.ptr(self.prim_bounds), self.n_primitives, self.max_node_primitives, C.byref(h))
         if rc != 0:
             raise RuntimeError(f"trace_bvh_build failed ({rc})")
         try:

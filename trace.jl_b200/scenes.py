@@ -59,7 +59,7 @@ def _spot_light_to_world(frm):
     return translate(_v3((4.5, 0, -101))) * translate(frm) * dir_to_z.inv()
 
 
-def _caustic_bvh(eta, ply=ASSET_PLY):
+def _caustic_bvh(eta, ply=ASSET_PLY, builder="reference", max_node_primitives=1):
     glass = GlassMaterial(ConstantTexture(RGBSpectrum(1.0)), ConstantTexture(RGBSpectrum(1.0)), ConstantTexture(0.0),
                           ConstantTexture(0.0), ConstantTexture(eta), True)
     plastic = PlasticMaterial(ConstantTexture(RGBSpectrum(0.6399999857)), ConstantTexture(RGBSpectrum(0.1000000015)),
@@ -68,12 +68,12 @@ def _caustic_bvh(eta, ply=ASSET_PLY):
     floor = create_triangle_mesh(ShapeCore(translate(_v3((-10, 0, -87))), False), 2, [1, 2, 3, 1, 4, 3], 4,
                                  [(0, 0, 0), (0, 0, -30), (30, 0, -30), (30, 0, 0)], [(0, 1, 0)] * 4)
     prims = [PrimitiveBatch(triangles, glass)] + [GeometricPrimitive(t, plastic) for t in floor]
-    return BVHAccel(prims, 1)
+    return BVHAccel(prims, max_node_primitives, builder=builder)
 
 
-def caustic_glass(resolution=256, max_depth=5, filename=None, ply=ASSET_PLY):
+def caustic_glass(resolution=256, max_depth=5, filename=None, ply=ASSET_PLY, builder="reference", max_node_primitives=1):
     """docs/code/caustic_glass.jl:6-95 (C1).  SPPMIntegrator(camera, 0.075, ray_depth, 100, -1)."""
-    bvh = _caustic_bvh(1.25, ply)
+    bvh = _caustic_bvh(1.25, ply, builder, max_node_primitives)
     lights = [SpotLight(_spot_light_to_world((0, 2, 0)), RGBSpectrum(60.0), 30.0, 20.0)]
     scene = Scene(lights, bvh)
     film = _film(resolution, filename=filename)
@@ -82,9 +82,10 @@ def caustic_glass(resolution=256, max_depth=5, filename=None, ply=ASSET_PLY):
     return scene, camera, dict(initial_search_radius=0.075, max_depth=max_depth, n_iterations=100)
 
 
-def caustic_moving(shift=0.0, resolution=1024, filename=None, ply=ASSET_PLY, bvh=None):
+def caustic_moving(shift=0.0, resolution=1024, filename=None, ply=ASSET_PLY, bvh=None, builder="reference",
+                   max_node_primitives=1):
     """One frame of docs/code/caustic_moving.jl:5-103 (C4).  SPPMIntegrator(camera, 0.055, 5, 25, 1_250_000)."""
-    bvh = bvh or _caustic_bvh(1.2, ply)
+    bvh = bvh or _caustic_bvh(1.2, ply, builder, max_node_primitives)
     lights = [PointLight(translate(_v3((2.5, 10, -100))), RGBSpectrum(1.0) * 20.0),
               SpotLight(_spot_light_to_world((0, 0.5 + shift, 0)), RGBSpectrum(0.988235, 0.972549, 0.57647) * 60.0, 30.0, 20.0)]
     scene = Scene(lights, bvh)
@@ -134,7 +135,7 @@ def _heightfield(cells, x0=-10.0, x1=10.0, z0=-30.0, z1=-10.0):
 
 
 def tessellated(cells=600, stacks=266, slices=264, res=(1920, 1080), window=((-50.0, -28.125), (50.0, 28.125)),
-                filename=None):
+                filename=None, builder="reference", max_node_primitives=1):
     """Synthetic "tess-1M" (C3, defaults: 999 840 triangles) / "tess-10M" (C5: cells=1900, stacks=835, slices=834,
     res=(4096, 4096), window=((-50,-50),(50,50)))  — SURVEY.md §8d.  WhittedIntegrator depth 5 / 8."""
     ident = ShapeCore(Transformation(), False)
@@ -148,7 +149,7 @@ def tessellated(cells=600, stacks=266, slices=264, res=(1920, 1080), window=((-5
     for center, mat in (((-2.5, 2.0, -20.0), glass), ((2.5, 2.0, -20.0), mirror)):
         v, n, idx = _uv_sphere(center, 2.0, stacks, slices)
         prims.append(PrimitiveBatch(TriangleSet(ident, TriangleMesh(ident.object_to_world, len(idx), idx.reshape(-1), len(v), v, n)), mat))
-    bvh = BVHAccel(prims, 1)
+    bvh = BVHAccel(prims, max_node_primitives, builder=builder)
     scene = Scene([PointLight(translate(_v3((0, 12, -10))), RGBSpectrum(400.0))], bvh)
     film = _film(res[0], res[1], filename=filename)
     camera = PerspectiveCamera(look_at(_v3((0, 14, 15)), _v3((-16, -18, -20)), _v3((0, 1, 0))),
