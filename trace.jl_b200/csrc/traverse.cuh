@@ -192,7 +192,8 @@ struct HitRecord {
 // Measured and rejected on B200 (profiles/r1_experiments.md): box-testing both children at their parent (0.7x), a
 // min/max reformulation of the slab test with fewer instructions (0.75-0.98x), persistent warps with dynamic ray
 // fetch (0.85x, kept below as option "persist"), a "while-while" loop whose lanes meet before testing primitives (0.32x:
-// lanes standing on a leaf wait for the longest box-test walk of the warp), prefetching the pushed far child (0.98x).
+// lanes standing on a leaf wait for the longest box-test walk of the warp), prefetching the pushed far child (0.98x),
+// keeping the first 12 / 16 / 24 stack entries in shared memory (0.86-0.90x).
 template <int SLAB, bool ANY, bool COUNT>
 __device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3 d, float tmax, HitRecord& out,
                                          unsigned long long* counters, int* error_flag) {
