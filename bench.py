@@ -429,6 +429,31 @@ def main():
                          "config": {"workload": name, "photons_per_iteration": sess.photons, "max_depth": kw["max_depth"],
                                     "primitives": int(s_scene.aggregate.n_primitives)}})
             sess.close()
+        if world > 1:
+            # self-check of the sharded SPPM path on the real collectives: a small render over all ranks against the same
+            # render on rank 0 alone (second context, world 1); the sharding must not change the image beyond the order
+            # of the float flux atomics
+            c_scene, c_cam, ckw = T.scenes.shadows(resolution=160)
+            sess = D.SPPMSession(ctx, c_scene, c_cam, ckw["initial_search_radius"], ckw["max_depth"], -1, 0x5EED0001, rank, world)
+            for _ in range(4):
+                sess.step()
+            img_sharded = sess.image()
+            sess.close()
+            check = None
+            if rank == 0:
+                solo = T.Context(local, stream=work_stream.cuda_stream)
+                s1 = D.SPPMSession(solo, c_scene, c_cam, ckw["initial_search_radius"], ckw["max_depth"], -1, 0x5EED0001, 0, 1)
+                for _ in range(4):
+                    s1.step()
+                img_solo = s1.image()
+                s1.close()
+                solo.close()
+                err = float(np.abs(img_sharded - img_solo).max())
+                check = {"workload": "sppm-shadows-160, 4 iterations", "max_abs_diff_vs_one_gpu": err, "image_max": float(img_solo.max()),
+                         "ok": bool(np.allclose(img_sharded, img_solo, rtol=3e-4, atol=1e-6))}
+            sppm.append({"sharded_vs_single_gpu_check": check})
+            ctx.set_option("world", world)
+            ctx.set_option("rank", rank)
         ctx.upload(scene)
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample of the same workload

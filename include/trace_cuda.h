@@ -153,11 +153,15 @@ void        trace_destroy(trace_ctx* ctx);
 const char* trace_last_error(const trace_ctx* ctx);
 /* options: "slab" 0 = literal reference slab test (bounds.jl:180-200), 1 = textbook slab (measured only: not
  *          hit-equivalent), 2 = guarded: literal AND a conservative interval test, hit-identical to 0 (default 2);
- *          "batch" camera samples per wavefront batch; "cap_percent" ray-queue capacity per bounce level in % of the
- *          batch (default 200; an overflowing batch is re-run in halves); "lanes" sub-batches of a Whitted render in
- *          flight concurrently on side streams (default 8); "persist" 0/1 persistent-warp traversal
- *          kernels (default 0); "count_nodes" 0/1; "time_kernels" 0/1;
- *          "rank"/"world" shard selection for renders (tiles / photons). */
+ *          "batch" camera samples in flight per Whitted render (default 2^26); "cap_percent" ray-queue capacity per
+ *          bounce level in % of the batch (default 200; an overflowing batch is re-run in halves); "lanes" sub-batches
+ *          of a Whitted render in flight concurrently on side streams (1..16, default 12); "deal" how tiles are dealt
+ *          to those batches (g > 0: groups of g tiles, -r: r tile rows, 0: contiguous bands; default -2); "graph" 0/1
+ *          replay the render as one CUDA graph (default 1; needs a non-default stream); "sppm_lanes" sub-ranges of
+ *          each SPPM pass on concurrent streams (0..8, default 0 = one camera + one photon lane); "persist" 0/1
+ *          persistent-warp traversal kernels (default 0); "count_nodes" 0/1; "time_kernels" 0/1 (per-launch CUDA
+ *          events; with TRACE_CUDA_TIMELINE=<file> they are also dumped); "rank"/"world" shard selection (Whitted: tiles
+ *          k % world; SPPM: image rows and, through the photon range arguments, photons). */
 int         trace_set_option(trace_ctx* ctx, const char* key, int64_t value);
 int         trace_get_stats(trace_ctx* ctx, trace_stats* out);
 int         trace_reset_stats(trace_ctx* ctx);

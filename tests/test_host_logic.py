@@ -103,6 +103,28 @@ def test_partition_helpers(T):
     assert D.n_sample_tiles(camera.film) == 65 * 65
 
 
+def test_sppm_storage_order(T):
+    """Row-sharded SPPM arrays: raster <-> storage is a bijection onto the non-padding slots, a rank's pixels fill its
+    contiguous slice, and world == 1 is the identity (the layout sppm.cu uses for the all-gather of visible points)."""
+    from trace_jl_b200 import distributed as D
+    for W, H, world in ((7, 5, 1), (7, 5, 2), (4, 9, 4), (3, 10, 8), (151, 151, 3)):
+        chunk, n = D.storage_layout(W, H, world)
+        assert chunk == -(-H // world) and n == world * chunk * W
+        seen = set()
+        for y in range(H):
+            for x in range(W):
+                s = D.raster_to_storage(x, y, W, H, world)
+                owner = y % world
+                assert owner * chunk * W <= s < (owner + 1) * chunk * W
+                assert D.storage_to_raster(s, W, H, world) == (x, y)
+                if world == 1:
+                    assert s == y * W + x
+                seen.add(s)
+        assert len(seen) == W * H
+        pads = [s for s in range(n) if D.storage_to_raster(s, W, H, world) is None]
+        assert len(pads) == n - W * H and not (set(pads) & seen)
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["REPO"]); sys.path.insert(0, os.path.join(os.environ["REPO"], "tests"))
@@ -129,6 +151,19 @@ D.allreduce_sum(t)
 full = np.zeros_like(film)
 osc.render_whitted(cam, fd, 2, 4, 9, full, threads=1)
 assert np.allclose(t.numpy(), full, rtol=1e-5, atol=1e-7), np.abs(t.numpy() - full).max()
+# SPPM: row-sharded per-pixel arrays in storage order - each rank fills its slice, the all-gather yields the whole image
+W_, H_ = 5, 7
+chunk, n_slots = D.storage_layout(W_, H_, world)
+buf = torch.full((n_slots,), -1.0)
+for s_ in range(rank * chunk * W_, (rank + 1) * chunk * W_):
+    xy = D.storage_to_raster(s_, W_, H_, world)
+    buf[s_] = float(xy[1] * W_ + xy[0]) if xy else -2.0
+parts = [torch.empty(chunk * W_) for _ in range(world)]
+dist.all_gather(parts, buf[rank * chunk * W_:(rank + 1) * chunk * W_].clone())
+whole = torch.cat(parts)
+for y_ in range(H_):
+    for x_ in range(W_):
+        assert whole[D.raster_to_storage(x_, y_, W_, H_, world)].item() == float(y_ * W_ + x_)
 # SPPM photon slices partition the iteration
 b, e = D.photon_range(1000, rank, world)
 cnt = torch.tensor([float(e - b)])

@@ -30,6 +30,29 @@ def photon_range(photons_per_iteration, rank, world):
     return (p * rank) // world, (p * (rank + 1)) // world
 
 
+def storage_layout(width, height, world):
+    """SPPM per-pixel arrays in STORAGE order (must match sppm.cu: storage_to_raster / raster_to_storage): image row y
+    belongs to rank y % world and is that rank's local row y // world; every rank's rows are contiguous and padded to
+    chunk_rows = ceil(height / world) rows, so rank r owns the slice [r, r + 1) * chunk_rows * width of every array.
+    Returns (chunk_rows, n_slots)."""
+    chunk_rows = (int(height) + int(world) - 1) // int(world)
+    return chunk_rows, int(world) * chunk_rows * int(width)
+
+
+def raster_to_storage(x, y, width, height, world):
+    chunk_rows, _ = storage_layout(width, height, world)
+    return ((y % world) * chunk_rows + y // world) * width + x
+
+
+def storage_to_raster(slot, width, height, world):
+    """(x, y) of a storage slot, or None for a padding slot."""
+    chunk_rows, _ = storage_layout(width, height, world)
+    row, x = divmod(int(slot), int(width))
+    owner, local = divmod(row, chunk_rows)
+    y = local * world + owner
+    return (x, y) if y < height else None
+
+
 def n_sample_tiles(film):
     sb = film.get_sample_bounds()
     ext = sb.p_max - sb.p_min
@@ -112,6 +135,7 @@ class SPPMSession:
         ctx.check(ctx.lib.trace_sppm_begin(ctx.h, C.byref(cam), C.byref(fd), float(initial_search_radius), int(max_depth),
                                            self.photons, C.c_uint64(seed)))
         self.buffers = None
+        self._vp_recv = None
         if world > 1:
             dev = f"cuda:{torch.cuda.current_device()}"
             self.buffers = []
@@ -127,6 +151,21 @@ class SPPMSession:
         n = t.numel() // self.world
         dist.all_gather_into_tensor(t, t[self.rank * n:(self.rank + 1) * n].clone(), group=self.group)
 
+    def _gather_visible_points(self):
+        """ONE all-gather for the five visible-point arrays: this rank's five slices are packed into one send buffer,
+        gathered as [world][5][slice], and scattered back into the arrays' rank slices (two small copy kernels instead
+        of four more collectives, whose launch latency dominates at these sizes)."""
+        import torch
+        import torch.distributed as dist
+        arrays = self.buffers[2:7]
+        n = arrays[0].numel() // self.world
+        send = torch.stack([a[self.rank * n:(self.rank + 1) * n] for a in arrays])          # [5][n]
+        if self._vp_recv is None:
+            self._vp_recv = torch.empty((self.world, len(arrays), n), dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(self._vp_recv, send, group=self.group)
+        for k, a in enumerate(arrays):
+            a.view(self.world, n).copy_(self._vp_recv[:, k, :])
+
     def step(self):
         """One SPPM iteration (sppm.jl:153-165) over all ranks."""
         self.iteration += 1
@@ -136,8 +175,7 @@ class SPPMSession:
         ctx.check(ctx.lib.trace_sppm_camera_pass(ctx.h, self.iteration))
         if self.world > 1:
             with _Fence(ctx):
-                for which in range(2, 7):
-                    self._all_gather(which)
+                self._gather_visible_points()
             ctx.check(ctx.lib.trace_sppm_build_grid(ctx.h))
         ctx.check(ctx.lib.trace_sppm_photon_pass(ctx.h, self.iteration, b, e))
         if self.world > 1:
