@@ -33,7 +33,6 @@ __host__ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
 __device__ __forceinline__ float length3(float3 a) { return sqrtf((a.x * a.x + a.y * a.y) + a.z * a.z); }
 __device__ __forceinline__ float3 normalize3(float3 a) { float inv = 1.0f / length3(a); return f3(inv * a.x, inv * a.y, inv * a.z); }
 __device__ __forceinline__ bool is_black3(float3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
-__device__ __forceinline__ float comp3(float3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 __device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
 __device__ __forceinline__ float4 f4(float3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return x > hi ? hi : (x < lo ? lo : x); }

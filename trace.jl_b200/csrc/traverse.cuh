@@ -15,7 +15,6 @@ struct RayPrep {            // quantities that depend on the ray only
     float3 o, d, inv;
     bool nx, ny, nz;
     int kz;                 // permutation of the triangle test
-    float ox, oy, oz;       // o permuted
     float Sx, Sy, Sz;       // shear
     float mx, my, mz;       // SLAB 2: per-axis slack of the conservative interval, in units of t
 };
@@ -43,9 +42,9 @@ __device__ __forceinline__ RayPrep prepare_ray(float3 o, float3 d, float scene_s
     if (az > am) { kz = 2; }
     r.kz = kz;
     float dx, dy, dz;
-    if (kz == 0)      { dx = d.y; dy = d.z; dz = d.x; r.ox = o.y; r.oy = o.z; r.oz = o.x; }
-    else if (kz == 1) { dx = d.z; dy = d.x; dz = d.y; r.ox = o.z; r.oy = o.x; r.oz = o.y; }
-    else              { dx = d.x; dy = d.y; dz = d.z; r.ox = o.x; r.oy = o.y; r.oz = o.z; }
+    if (kz == 0)      { dx = d.y; dy = d.z; dz = d.x; }
+    else if (kz == 1) { dx = d.z; dy = d.x; dz = d.y; }
+    else              { dx = d.x; dy = d.y; dz = d.z; }
     float denom = 1.0f / dz;
     r.Sx = -dx * denom; r.Sy = -dy * denom; r.Sz = denom;
     const float slack = TR_GUARD_REL * fmaxf(scene_scale, fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z))));
