@@ -243,6 +243,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) k_grid_insert(SppmLaunch L) {
     const GridParams g = *L.grid;
     if (!g.valid) return;
+    const int lane = threadIdx.x & 31;
     for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.nstore; pix += gridDim.x * blockDim.x) {
         if (L.vpC[pix].w == 0.0f) continue;
         const float4 A = L.vpA[pix];
@@ -252,9 +253,18 @@ __global__ void __launch_bounds__(256) k_grid_insert(SppmLaunch L) {
         to_grid(g, f3(A.x + r, A.y + r, A.z + r), c1);
         for (int z = c0[2]; z <= c1[2]; ++z) for (int y = c0[1]; y <= c1[1]; ++y) for (int x = c0[0]; x <= c1[0]; ++x) {
             const unsigned int h = grid_hash(x, y, z, (unsigned int)L.npix);
-            if (!FILL) atomicAdd(&L.cell_start[h], 1u);
+            // neighbouring pixels fall into the same cells (a cell holds thousands of visible points where the pixel
+            // footprint is far below the radius): the lanes that hit the same cell right now issue ONE atomic
+            const unsigned int active = __activemask();
+            const unsigned int peers = __match_any_sync(active, h);
+            const int leader = __ffs(peers) - 1;
+            const unsigned int n_peers = (unsigned int)__popc(peers);
+            if (!FILL) { if (lane == leader) atomicAdd(&L.cell_start[h], n_peers); }
             else {
-                const unsigned int slot = atomicAdd(&L.cell_cursor[h], 1u);
+                unsigned int base = 0;
+                if (lane == leader) base = atomicAdd(&L.cell_cursor[h], n_peers);
+                base = __shfl_sync(peers, base, leader);
+                const unsigned int slot = base + (unsigned int)__popc(peers & ((1u << lane) - 1u));
                 if (slot < L.items_cap) { L.cell_items[slot] = (unsigned int)pix; L.cell_vp[slot] = make_float4(A.x, A.y, A.z, A.w); }
             }
         }
