@@ -337,16 +337,14 @@ def main():
     host_film = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
     cam_pod, fd = camera.pod(), camera.film.desc()
 
+    sharded_host = D.ShardedWhittedRenderer(ctx, scene, camera, rank, world) if world > 1 else None
+
     def e2e_step(i):
         if world == 1:
             ctx.check(ctx.lib.trace_render_whitted(ctx.h, C.byref(cam_pod), C.byref(fd), spp, depth, C.c_uint64(2000 + i),
                                                    C.c_void_p(host_film.data_ptr())))
         else:
-            film_dev.copy_(host_film, non_blocking=True)
-            D.render_whitted_sharded(ctx, scene, camera, spp, depth, 2000 + i, film_dev, rank, world)
-            if rank == 0:
-                host_film.copy_(film_dev, non_blocking=True)
-            torch.cuda.synchronize()
+            sharded_host.render(host_film if rank == 0 else None, spp, depth, 2000 + i)
 
     e2e_step(0)
     barrier()

@@ -116,6 +116,41 @@ def render_whitted_sharded(ctx, scene, camera, spp, max_depth, seed, film_tensor
     return film_tensor
 
 
+class ShardedWhittedRenderer:
+    """Whitted render over `world` ranks with a HOST film (the reference's accumulate-into-film semantics, film.jl:182-193):
+    every rank renders its tiles into a zeroed device film, one reduce(sum) to rank 0, and rank 0 adds the caller's
+    film - uploaded on a copy stream WHILE the render runs - and copies the sum back.  `host_film` (rank 0; pinned for
+    the copies to be asynchronous) is float32 [H, W, 4]; other ranks pass None."""
+
+    def __init__(self, ctx, scene, camera, rank=0, world=1, group=None):
+        import torch
+        self.ctx, self.scene, self.camera, self.rank, self.world, self.group = ctx, scene, camera, rank, world, group
+        h, w = camera.film.pixels.shape[:2]
+        dev = f"cuda:{torch.cuda.current_device()}"
+        self.film_dev = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+        self.staging = torch.zeros((h, w, 4), dtype=torch.float32, device=dev) if rank == 0 else None
+        self.copy_stream = torch.cuda.Stream() if rank == 0 else None
+        self.uploaded = torch.cuda.Event() if rank == 0 else None
+
+    def render(self, host_film, spp, max_depth, seed):
+        import torch
+        cur = torch.cuda.current_stream()
+        if self.rank == 0:
+            self.copy_stream.wait_stream(cur)                    # (the previous render's add_ has read `staging`)
+            with torch.cuda.stream(self.copy_stream):
+                self.staging.copy_(host_film, non_blocking=True)
+                self.uploaded.record()
+        self.film_dev.zero_()
+        render_whitted_sharded(self.ctx, self.scene, self.camera, spp, max_depth, seed, self.film_dev, self.rank, self.world,
+                               self.group, reduce=True)
+        if self.rank == 0:
+            cur.wait_event(self.uploaded)
+            self.film_dev.add_(self.staging)
+            host_film.copy_(self.film_dev, non_blocking=True)
+        cur.synchronize()
+        return host_film
+
+
 class SPPMSession:
     """Stepwise SPPM (trace_sppm_begin / camera_pass / photon_pass / update / image) with photon sharding."""
 
