@@ -589,6 +589,14 @@ extern "C" int ref_microfacet_reflection_sample(const float r[3], float ax, floa
     put_sample(lobe_sample(l, V3(wo[0], wo[1], wo[2]), u[0], u[1]), out);
     return 0;
 }
+extern "C" int ref_microfacet_transmission_sample(const float t[3], float ax, float ay, float ea, float eb,
+                                                  const float wo[3], const float u[2], float out[8]) {
+    Lobe l = mk_lobe(L_MICRO_TRANS, BSDF_TRANSMISSION | BSDF_GLOSSY);          // microfacet.jl:261-278
+    l.t = RGB(t[0], t[1], t[2]); l.eta_a = ea; l.eta_b = eb; l.fresnel = 1; l.fi = ea; l.ft = eb;
+    tr_alphas(l, ax, ay);
+    put_sample(lobe_sample(l, V3(wo[0], wo[1], wo[2]), u[0], u[1]), out);
+    return 0;
+}
 static void canonical_bsdf(const trace_material* m, int mode, BSDF& b) {
     SurfaceInteraction si;
     si.p = V3(0.0f); si.wo = V3(0, 0, 1); si.ng = V3(0, 0, 1); si.ns = V3(0, 0, 1); si.sh_dpdu = V3(1, 0, 0);

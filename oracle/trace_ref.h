@@ -66,6 +66,8 @@ int   ref_fresnel_specular_sample(const float r[3], const float t[3], float eta_
                                   const float wo[3], const float u[2], float out[8]);
 int   ref_microfacet_reflection_sample(const float r[3], float ax, float ay, int fresnel_kind /*0 noop,1 dielectric*/,
                                        float eta_i, float eta_t, const float wo[3], const float u[2], float out[8]);
+int   ref_microfacet_transmission_sample(const float t[3], float ax, float ay, float eta_a, float eta_b,
+                                         const float wo[3], const float u[2], float out[8]);   /* microfacet.jl:307-320 */
 float ref_lanczos(float px, float py, float rx, float ry, float tau);               /* filter.jl:3-23 */
 float ref_radical_inverse(int64_t base_index, uint64_t a);                           /* sampler/sampling.jl:43-60 */
 float ref_roughness_to_alpha(float r);                                               /* microfacet.jl:79-84 */

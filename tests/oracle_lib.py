@@ -43,6 +43,7 @@ def lib():
         L.ref_fresnel_dielectric.argtypes = [C.c_float, C.c_float, C.c_float]
         L.ref_fresnel_specular_sample.argtypes = [P, P, C.c_float, C.c_float, P, P, P]
         L.ref_microfacet_reflection_sample.argtypes = [P, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, P, P, P]
+        L.ref_microfacet_transmission_sample.argtypes = [P, C.c_float, C.c_float, C.c_float, C.c_float, P, P, P]
         L.ref_lanczos.restype = C.c_float
         L.ref_lanczos.argtypes = [C.c_float] * 5
         L.ref_radical_inverse.restype = C.c_float

@@ -161,6 +161,15 @@ def test_microfacet_reflection_normal_incidence():
     assert approx(out[:3], [0, 0, 1])
 
 
+def test_microfacet_transmission_normal_incidence():
+    """test/test_materials.jl:56-68: TrowbridgeReitz(1, 1), eta 1 -> 2, wo = +z, u = (0, 0)  =>  wi = (0, 0, -1)."""
+    out = np.zeros(8, np.float32)
+    one = f3([1, 1, 1])
+    lib().ref_microfacet_transmission_sample(p(one), 1.0, 1.0, 1.0, 2.0, p(f3([0, 0, 1])), p(f3([0, 0])), p(out))
+    assert approx(out[:3], [0, 0, -1])
+    assert int(out[7]) == -1                # the reference's sample_f returns `nothing` as the sampled type (:319)
+
+
 def test_bxdf_type_flags(T):
     import ctypes as C
     # SpecularReflection & (SPECULAR|REFLECTION); SpecularTransmission & (SPECULAR|TRANSMISSION); FresnelSpecular & all three
