@@ -11,6 +11,8 @@ kw_res = dict(resolution=res) if res else {}
 if os.environ.get("BUILDER"):
     kw_res.update(builder=os.environ["BUILDER"], max_node_primitives=int(os.environ.get("MNP", "1")))
 scene, camera, kw = getattr(T.scenes, name)(**kw_res)
+if os.environ.get("DEPTH"):
+    kw["max_depth"] = int(os.environ["DEPTH"])
 torch.cuda.set_device(0)
 _s = torch.cuda.Stream(device=0)
 torch.cuda.set_stream(_s)
@@ -30,7 +32,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 st = ctx.stats()
-print(f"{name} builder={os.environ.get('BUILDER', 'reference')}/{os.environ.get('MNP', '1')} sppm_lanes={os.environ.get('SPPM_LANES', '0')} persist={os.environ.get('PERSIST', '0')}: {iters / ms * 1e3:.2f} it/s  ({ms / iters:.3f} ms/it)  rays/it extend {st['rays_extend'] / iters:.0f} shadow {st['rays_shadow'] / iters:.0f} "
+print(f"{name} depth={kw['max_depth']} builder={os.environ.get('BUILDER', 'reference')}/{os.environ.get('MNP', '1')} sppm_lanes={os.environ.get('SPPM_LANES', '0')} persist={os.environ.get('PERSIST', '0')}: {iters / ms * 1e3:.2f} it/s  ({ms / iters:.3f} ms/it)  rays/it extend {st['rays_extend'] / iters:.0f} shadow {st['rays_shadow'] / iters:.0f} "
       f"deposits/it {st['sppm_deposits'] / iters:.0f} launches/it {st['kernel_launches'] / iters:.1f} photons/it {sess.photons}")
 if os.environ.get("COUNT_NODES"):
     ctx.set_option("count_nodes", 1)
