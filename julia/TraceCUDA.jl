@@ -91,7 +91,134 @@ function flatten_nodes(bvh::Trace.BVHAccel)
         end
     end
 end
-# (primitive / material / light flattening is mechanical: see scene.py; nested BVHAccel primitives are spliced in place.)
+
+# constants of include/trace_cuda.h
+const PRIM_TRIANGLE, PRIM_SPHERE = UInt32(0), UInt32(1)
+const MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_PLASTIC = UInt32(0), UInt32(1), UInt32(2), UInt32(3)
+const LIGHT_POINT, LIGHT_SPOT, LIGHT_DIRECTIONAL = UInt32(0), UInt32(1), UInt32(2)
+const NO_MATERIAL = 0xFFFFFFFF
+
+# Only constant textures are supported on the device (the three docs/code scenes use nothing else).
+texval(t::Trace.ConstantTexture) = t.value
+texval(t) = error("TraceCUDA: only ConstantTexture is supported on the GPU path, got $(typeof(t))")
+rgb3(s::Trace.RGBSpectrum) = (s.c[1], s.c[2], s.c[3])
+const ZERO3 = (0f0, 0f0, 0f0)
+
+material_pod(m::Trace.MatteMaterial) = MaterialP(MAT_MATTE, rgb3(texval(m.Kd)), ZERO3, 1f0, Float32(texval(m.σ)), 0f0, 0)
+material_pod(m::Trace.MirrorMaterial) = MaterialP(MAT_MIRROR, rgb3(texval(m.Kr)), ZERO3, 1f0, 0f0, 0f0, 0)
+material_pod(m::Trace.GlassMaterial) = MaterialP(MAT_GLASS, rgb3(texval(m.Kr)), rgb3(texval(m.Kt)), Float32(texval(m.index)),
+    Float32(texval(m.u_roughness)), Float32(texval(m.v_roughness)), UInt32(m.remap_roughness))
+material_pod(m::Trace.PlasticMaterial) = MaterialP(MAT_PLASTIC, rgb3(texval(m.Kd)), rgb3(texval(m.Ks)), 1f0,
+    Float32(texval(m.roughness)), 0f0, UInt32(m.remap_roughness))
+
+light_pod(l::Trace.PointLight) = LightP(LIGHT_POINT, rowmajor(l.light_to_world.m), rowmajor(l.light_to_world.inv_m),
+    rgb3(l.i), Tuple(l.position), 0f0, 0f0)
+light_pod(l::Trace.SpotLight) = LightP(LIGHT_SPOT, rowmajor(l.light_to_world.m), rowmajor(l.light_to_world.inv_m),
+    rgb3(l.i), Tuple(l.position), l.cos_total_width, l.cos_falloff_start)
+# DirectionalLight: `position` carries the direction, `cos_total_width` the world radius (0 until preprocess!, as in the reference)
+light_pod(l::Trace.DirectionalLight) = LightP(LIGHT_DIRECTIONAL, rowmajor(l.light_to_world.m), rowmajor(l.light_to_world.inv_m),
+    rgb3(l.i), Tuple(l.direction), l.world_radius, 0f0)
+
+flips(core::Trace.ShapeCore) = core.reverse_orientation != core.transform_swaps_handedness
+
+# Everything trace_scene_upload needs, as Julia arrays kept alive by the caller (GC.@preserve) during the ccall.
+mutable struct FlatScene
+    nodes::Vector{BVHNode}
+    prims::Vector{Prim}
+    tri_vertices::Vector{Float32}      # [n_tris][3][3], world space
+    tri_normals::Vector{Float32}       # [n_tris][3][3]
+    tri_flags::Vector{UInt8}           # bit 0: flip orientation, bit 1: has per-vertex normals
+    spheres::Vector{SphereP}
+    materials::Vector{MaterialP}
+    lights::Vector{LightP}
+    material_ids::IdDict{Any,UInt32}
+    n_original::UInt32                 # running "caller's order" primitive number
+end
+FlatScene() = FlatScene(BVHNode[], Prim[], Float32[], Float32[], UInt8[], SphereP[], MaterialP[], LightP[], IdDict{Any,UInt32}(), 0)
+
+function material_id!(fs::FlatScene, m)
+    m === nothing && return NO_MATERIAL          # fine for intersect!/intersect_p; the integrators refuse such scenes
+    get!(fs.material_ids, m) do
+        push!(fs.materials, material_pod(m))
+        UInt32(length(fs.materials) - 1)
+    end
+end
+
+# one reference primitive -> one trace_prim row (shape data appended to the shape tables)
+function prim_row!(fs::FlatScene, p::Trace.GeometricPrimitive{Trace.Triangle})
+    t = p.shape
+    ids = t.mesh.indices[t.i:t.i + 2]
+    for k in ids
+        append!(fs.tri_vertices, Float32.(Tuple(t.mesh.vertices[k])))
+    end
+    has_n = t.mesh.normals !== nothing
+    for k in ids
+        append!(fs.tri_normals, has_n ? Float32.(Tuple(t.mesh.normals[k])) : ZERO3)
+    end
+    push!(fs.tri_flags, UInt8(flips(t.core)) | (UInt8(has_n) << 1))
+    row = Prim(PRIM_TRIANGLE, UInt32(length(fs.tri_flags) - 1), material_id!(fs, p.material), fs.n_original)
+    fs.n_original += 1
+    row
+end
+function prim_row!(fs::FlatScene, p::Trace.GeometricPrimitive{Trace.Sphere})
+    s = p.shape
+    push!(fs.spheres, SphereP(rowmajor(s.core.object_to_world.m), rowmajor(s.core.object_to_world.inv_m), s.radius,
+                              s.z_min, s.z_max, s.θ_min, s.θ_max, s.ϕ_max, UInt32(flips(s.core)), 0))
+    row = Prim(PRIM_SPHERE, UInt32(length(fs.spheres) - 1), material_id!(fs, p.material), fs.n_original)
+    fs.n_original += 1
+    row
+end
+
+# Emits bvh's LinearBVH array (preorder, first child = parent + 1) into fs.nodes / fs.prims, 0-based.  A BVHAccel used as
+# a primitive (test/test_intersection.jl:137-138) is spliced in place of the leaf that holds it, so the device walks
+# the same boxes in the same order as the reference's recursive intersect!.
+function emit!(fs::FlatScene, bvh::Trace.BVHAccel, i::Int = 1)
+    n = bvh.nodes[i]
+    if n isa Trace.LinearBVHLeaf
+        held = bvh.primitives[n.primitives_offset:n.primitives_offset + n.n_primitives - 1]
+        if any(p -> p isa Trace.BVHAccel, held)
+            length(held) == 1 || error("TraceCUDA: a leaf mixing a nested BVHAccel with other primitives")
+            return emit!(fs, held[1], 1)
+        end
+        push!(fs.nodes, BVHNode(Tuple(n.bounds.p_min), Tuple(n.bounds.p_max), UInt32(length(fs.prims)), 0xC0000000 | n.n_primitives))
+        for p in held
+            push!(fs.prims, prim_row!(fs, p))
+        end
+    else
+        slot = length(fs.nodes) + 1
+        push!(fs.nodes, BVHNode(Tuple(n.bounds.p_min), Tuple(n.bounds.p_max), 0, UInt32(n.split_axis - 1) << 30))
+        emit!(fs, bvh, i + 1)
+        second = UInt32(length(fs.nodes))                       # 0-based index of the node emitted next
+        emit!(fs, bvh, Int(n.second_child_offset))
+        fs.nodes[slot] = BVHNode(fs.nodes[slot].bmin, fs.nodes[slot].bmax, second, fs.nodes[slot].meta)
+    end
+    nothing
+end
+# `original` (what trace_intersect reports, + 1) numbers the primitives in emission order.  Leaves are emitted in
+# preorder and the reference's build appends primitives to `bvh.primitives` in that same order (`ordered_primitives`, bvh.jl:97-104), so for
+# a BVHAccel without nested accelerators `original + 1` indexes `bvh.primitives` directly.  (The Python mirror still has
+# the Vector the caller handed to BVHAccel and numbers in that order instead.)
+
+function flatten(scene::Trace.Scene)
+    fs = FlatScene()
+    isempty(scene.aggregate.nodes) || emit!(fs, scene.aggregate)
+    append!(fs.lights, light_pod.(scene.lights))
+    fs
+end
+
+const UPLOADED = IdDict{Any,Tuple{Any,FlatScene}}()     # per context: the scene that is on the device + its flattening
+
+function upload!(ctx::Context, scene::Trace.Scene)
+    haskey(UPLOADED, ctx) && UPLOADED[ctx][1] === scene && return nothing      # already there (scenes are immutable)
+    fs = flatten(scene)
+    desc = SceneDesc(length(fs.nodes), pointer(fs.nodes), length(fs.prims), pointer(fs.prims),
+                     length(fs.tri_flags), pointer(fs.tri_vertices), pointer(fs.tri_normals), pointer(fs.tri_flags),
+                     length(fs.spheres), pointer(fs.spheres), length(fs.materials), pointer(fs.materials),
+                     length(fs.lights), pointer(fs.lights))
+    GC.@preserve fs check(ctx, ccall((:trace_scene_upload, LIB), Cint, (Ptr{Cvoid}, Ref{SceneDesc}), ctx.h, desc))
+    UPLOADED[ctx] = (scene, fs)
+    nothing
+end
 
 # ---- the two functors ------------------------------------------------------------------------------------------------
 struct GPU{I<:Trace.Integrator}
@@ -163,6 +290,5 @@ function intersect!(ctx::Context, o::Matrix{Float32}, d::Matrix{Float32}, t_max:
     prim, bary            # t_max now holds the hit distances, like ray.t_max after intersect!
 end
 
-function upload! end      # SceneDesc assembly + ccall(:trace_scene_upload, ...): see trace.jl_b200/scene.py
 
 end # module
