@@ -39,3 +39,46 @@ def test_shadows_landmarks(T):
     # floor / wall seam near 75 % of the height
     wall = (prim == 7) | (prim == 8)
     assert 0.70 * 1024 < row_from_top[wall].max() < 0.80 * 1024
+
+
+def test_tess_1m_framing_matches_the_survey(T):
+    """C3 ("tess-1M", BASELINE.json configs[2]) is a synthetic scene defined by SURVEY.md §8d, which also states where it
+    must land on the 1920x1080 film under the reference's off-axis frustum quirk (Q1): the scene's bounding box
+    projects to pixels x in [134, 1859], y in [54, 960] and the two spheres' centres to ~(765, 659) and (1080, 613)
+    (the survey's own float32 emulation of the literal matrices).  The generator + host camera algebra + the oracle's
+    closest hit reproduce those numbers (a coarser tessellation has the same extents)."""
+    cells, stacks, slices = 120, 66, 64
+    scene, camera, _ = T.scenes.tessellated(cells=cells, stacks=stacks, slices=slices)
+    flat = scene.flatten()
+    # bounding-box corners -> raster, through the inverse of the (quirky) raster -> camera map, which is affine in (x, y)
+    lo, hi = flat.nodes[0]["bmin"].astype(np.float64), flat.nodes[0]["bmax"].astype(np.float64)
+    w2c = np.linalg.inv(camera.camera_to_world.m.astype(np.float64))
+    base = camera.raster_to_camera.points(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)).astype(np.float64)
+    A = np.stack([base[1] - base[0], base[2] - base[0], base[0]], axis=1)          # p_cam = A @ [x, y, 1]
+    pix = []
+    for cx in (lo[0], hi[0]):
+        for cy in (lo[1], hi[1]):
+            for cz in (lo[2], hi[2]):
+                c = (w2c @ np.array([cx, cy, cz, 1.0]))[:3]
+                x, y, _ = np.linalg.solve(np.stack([A[:, 0], A[:, 1], -c], axis=1), -A[:, 2])
+                pix.append((x, y))
+    pix = np.array(pix)
+    assert abs(pix[:, 0].min() - 134) < 1 and abs(pix[:, 0].max() - 1859) < 1
+    assert abs(pix[:, 1].min() - 54) < 1 and abs(pix[:, 1].max() - 960) < 1
+    # sphere silhouettes by closest hit
+    osc = oracle_lib.OracleScene(flat)
+    step = 4
+    X, Y = np.meshgrid(np.arange(1, 1921, step, dtype=np.float32) + 0.5, np.arange(1, 1081, step, dtype=np.float32) + 0.5, indexing="xy")
+    pts = camera.raster_to_camera.points(np.stack([X.ravel(), Y.ravel(), np.zeros(X.size, np.float32)], 1))
+    d = pts / np.linalg.norm(pts, axis=1, keepdims=True)
+    d = (d @ camera.camera_to_world.m[:3, :3].T).astype(np.float32)
+    o = np.tile(camera.camera_to_world.point([0, 0, 0])[None], (len(d), 1)).astype(np.float32)
+    prim, _, _ = osc.intersect(o, d)
+    ids = prim.reshape(X.shape).astype(np.int64) - 1
+    n_hf = 2 * cells * cells
+    n_sphere = (len(flat.prims) - n_hf) // 2
+    for lo_id, expect in ((n_hf, (765, 659)), (n_hf + n_sphere, (1080, 613))):
+        m = (ids >= lo_id) & (ids < lo_id + n_sphere)
+        assert m.sum() > 1000
+        cx, cy = (X[m].min() + X[m].max()) / 2, (Y[m].min() + Y[m].max()) / 2
+        assert abs(cx - expect[0]) < 6 and abs(cy - expect[1]) < 6, (cx, cy)
