@@ -82,3 +82,27 @@ def test_tess_1m_framing_matches_the_survey(T):
         assert m.sum() > 1000
         cx, cy = (X[m].min() + X[m].max()) / 2, (Y[m].min() + Y[m].max()) / 2
         assert abs(cx - expect[0]) < 6 and abs(cy - expect[1]) < 6, (cx, cy)
+
+
+def _bbox_on_film(camera, flat):
+    lo, hi = flat.nodes[0]["bmin"].astype(np.float64), flat.nodes[0]["bmax"].astype(np.float64)
+    w2c = np.linalg.inv(camera.camera_to_world.m.astype(np.float64))
+    base = camera.raster_to_camera.points(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)).astype(np.float64)
+    A = np.stack([base[1] - base[0], base[2] - base[0], base[0]], axis=1)
+    pix = []
+    for cx in (lo[0], hi[0]):
+        for cy in (lo[1], hi[1]):
+            for cz in (lo[2], hi[2]):
+                c = (w2c @ np.array([cx, cy, cz, 1.0]))[:3]
+                x, y, _ = np.linalg.solve(np.stack([A[:, 0], A[:, 1], -c], axis=1), -A[:, 2])
+                pix.append((x, y))
+    pix = np.array(pix)
+    return pix[:, 0].min(), pix[:, 0].max(), pix[:, 1].min(), pix[:, 1].max()
+
+
+def test_tess_10m_framing_matches_the_survey(T):
+    """C5 ("tess-10M", configs[4]): 4096x4096, window (-50,-50)-(50,50), same camera: SURVEY.md §8d puts the bounding box
+    at x in [229, 3910], y in [125, 2059]."""
+    scene, camera, _ = T.scenes.tessellated(cells=60, stacks=34, slices=32, res=(4096, 4096), window=((-50.0, -50.0), (50.0, 50.0)))
+    x0, x1, y0, y1 = _bbox_on_film(camera, scene.flatten())
+    assert abs(x0 - 229) < 1 and abs(x1 - 3910) < 1 and abs(y0 - 125) < 1 and abs(y1 - 2059) < 1
