@@ -286,3 +286,30 @@ def test_radical_inverse():
     assert abs(L.ref_radical_inverse(1, 1) - 1 / 3) < 1e-7 and abs(L.ref_radical_inverse(1, 5) - (2 / 3 + 1 / 9)) < 1e-6
     assert abs(L.ref_radical_inverse(2, 7) - (2 / 5 + 1 / 25)) < 1e-6
     assert L.ref_radical_inverse(3, 0) == 0.0
+
+
+def test_loose_slab_quirk_q26_work_counts(T):
+    """the reference's box test keeps the LARGER y far bound (bounds.jl:191), which makes it
+    accept far more boxes than a textbook slab test without changing any hit.  The survey's independent emulation of
+    the literal build + traversal on C1 measured ~406-520 box tests and ~48 triangle tests per ray with the literal
+    test against ~40 / ~2 with the textbook one (7 396 camera rays mixed with random rays), and 0 hit mismatches.
+    The restatement shows the same signature on the 86 x 86 camera-ray grid of C1: a restatement that had silently
+    "fixed" line 191 would sit at ~20 box tests per ray."""
+    scene, camera, _ = T.scenes.caustic_glass()
+    osc = __import__("oracle_lib").OracleScene(scene.flatten())
+    xs = np.arange(1, 257, 3, dtype=np.float32) + 0.5
+    X, Y = np.meshgrid(xs, xs, indexing="xy")
+    pts = camera.raster_to_camera.points(np.stack([X.ravel(), Y.ravel(), np.zeros(X.size, np.float32)], 1))
+    d = pts / np.linalg.norm(pts, axis=1, keepdims=True)
+    d = (d @ camera.camera_to_world.m[:3, :3].T).astype(np.float32)
+    o = np.tile(camera.camera_to_world.point([0, 0, 0])[None], (len(d), 1)).astype(np.float32)
+    assert len(o) == 7396
+    lit = osc.intersect(o, d, slab=0, counters=True)
+    std = osc.intersect(o, d, slab=1, counters=True)
+    grd = osc.intersect(o, d, slab=2, counters=True)
+    n = float(len(o))
+    assert 400 < lit[3][0] / n < 700 and 40 < lit[3][1] / n < 70          # measured 559.5 / 53.7
+    assert 10 < std[3][0] / n < 45 and 1.5 < std[3][1] / n < 3.0          # measured 19.8 / 2.17
+    assert grd[3][0] <= std[3][0] * 1.05                                  # the guarded test does the textbook amount of work
+    for other in (std, grd):                                              # ... and none of them changes a hit on this set
+        assert np.array_equal(lit[0], other[0]) and np.array_equal(lit[1].view(np.uint32), other[1].view(np.uint32))
