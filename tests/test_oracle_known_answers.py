@@ -311,5 +311,6 @@ def test_loose_slab_quirk_q26_work_counts(T):
     assert 400 < lit[3][0] / n < 700 and 40 < lit[3][1] / n < 70          # measured 559.5 / 53.7
     assert 10 < std[3][0] / n < 45 and 1.5 < std[3][1] / n < 3.0          # measured 19.8 / 2.17
     assert grd[3][0] <= std[3][0] * 1.05                                  # the guarded test does the textbook amount of work
+    assert 20 <= int(lit[3][2]) < 64                                      # deepest pending-node stack (survey: 27 seen; limit 64, bvh.jl:222)
     for other in (std, grd):                                              # ... and none of them changes a hit on this set
         assert np.array_equal(lit[0], other[0]) and np.array_equal(lit[1].view(np.uint32), other[1].view(np.uint32))
