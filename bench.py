@@ -320,6 +320,14 @@ def main():
             roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "extend_traffic.json"))).get(args.workload)
         except Exception:
             pass
+    try:
+        # what actually crosses the HBM interface (ncu dram bytes per launch) over the same live launch time: the gap to
+        # `achieved` is the share of the algorithmic bytes served by L1/L2
+        if roofline.get("traffic"):
+            roofline["dram_achieved_GBps"] = float(roofline["traffic"]) / (roofline["avg_launch_ms"] * 1e-3) / 1e9
+            roofline["dram_frac"] = roofline["dram_achieved_GBps"] / float(roofline["peak"])
+    except Exception:
+        pass
 
     # ---- per-rank breakdown of a step (separate, untimed-for-the-metric pass): render vs film reduce
     breakdown = None
