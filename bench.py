@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--persist", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=12)
+    ap.add_argument("--walk", type=int, default=1, help="traversal loop: 1 pair nodes (default), 0 one node per step (the reference loop)")
     ap.add_argument("--builder", default="reference", choices=["reference", "sah"],
                     help="BVH build: the reference's split logic (default, bit-identical tree) or the opt-in conventional SAH")
     ap.add_argument("--graph", type=int, default=1, help="replay the render as one CUDA graph (0: direct launches)")
@@ -212,6 +213,7 @@ def main():
     ctx = T.Context(local, stream=work_stream.cuda_stream)
     ctx.set_option("slab", args.slab)
     ctx.set_option("persist", args.persist)
+    ctx.set_option("walk", args.walk)
     ctx.set_option("lanes", args.lanes)
     ctx.set_option("graph", args.graph)
     if args.batch:

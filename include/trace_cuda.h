@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TRACE_ABI_VERSION 1
+#define TRACE_ABI_VERSION 2
 
 /* ---- BVH node, 32 bytes (LinearBVHLeaf / LinearBVHInterior, src/accel/bvh.jl:38-48) ----
  * interior: first child = self + 1, second child = `offset`; meta = split_axis << 30 (axis 0,1,2)
@@ -158,7 +158,11 @@ const char* trace_last_error(const trace_ctx* ctx);
  *          of a Whitted render in flight concurrently on side streams (1..16, default 12); "deal" how tiles are dealt
  *          to those batches (g > 0: groups of g tiles, -r: r tile rows, 0: contiguous bands; default -2); "graph" 0/1
  *          replay the render as one CUDA graph (default 1; needs a non-default stream); "sppm_lanes" sub-ranges of
- *          each SPPM pass on concurrent streams (0..8, default 0 = one camera + one photon lane); "persist" 0/1
+ *          each SPPM pass on concurrent streams (0..8, default 0 = one camera + one photon lane); "walk" traversal
+ *          loop: 1 = pair nodes (default: one 64-byte fetch serves both children's box tests and the far child is
+ *          pushed with its entry distance; same hits bit for bit), 0 = one node per step exactly as
+ *          src/accel/bvh.jl:221-257; "leaf_wait" 0/4/8/16/32 warp-synchronous variant of loop 0 with batched leaf
+ *          tests (measured slower, kept for the record); "film_mode" see trace_comm_init; "persist" 0/1
  *          persistent-warp traversal kernels (default 0); "count_nodes" 0/1; "time_kernels" 0/1 (per-launch CUDA
  *          events; with TRACE_CUDA_TIMELINE=<file> they are also dumped); "rank"/"world" shard selection (Whitted: tiles
  *          k % world; SPPM: image rows and, through the photon range arguments, photons). */
@@ -166,6 +170,27 @@ int         trace_set_option(trace_ctx* ctx, const char* key, int64_t value);
 int         trace_get_stats(trace_ctx* ctx, trace_stats* out);
 int         trace_reset_stats(trace_ctx* ctx);
 int         trace_synchronize(trace_ctx* ctx);
+
+/* ---- multi-GPU: one trace_ctx per GPU (one per process, or one per thread of a process), scene uploaded to each.
+ * The reference parallelises with Threads.@threads over 16x16 tiles (src/integrators/sampler.jl:24) and over photons
+ * (src/integrators/sppm.jl:328) into SHARED film / pixel arrays; across GPUs the sharing becomes the two collectives of
+ * SURVEY.md 8e, which the library runs itself on NCCL (bound at run time with dlopen; TRACE_NCCL_LIB overrides the
+ * path).  Rank 0 creates an id, passes the TRACE_COMM_ID_BYTES bytes to the other ranks out of band, and all ranks
+ * call trace_comm_init (collective: returns when all `world` ranks have joined).  Afterwards, on every rank,
+ *   trace_render_whitted[_device] renders the rank's tiles (k % world == rank) and sums the films:
+ *       option "film_mode" 0 (default): rank 0's film receives the whole image, other ranks' films are left untouched
+ *                                       (their film pointer may be NULL in the host-buffer call);
+ *       option "film_mode" 1: pixel i of the film (row-major) is delivered to rank i / ceil(n_pixels / world): every rank
+ *                             adds its contiguous band to ITS film - threads of one process pass the same host film and
+ *                             each GPU writes its band, processes each hold a band;
+ *   trace_render_sppm shards camera paths by image rows and photons by index range, all-gathers the visible points and
+ *       all-reduces (Phi, M) every iteration; every rank returns the complete image in rgb_out.
+ * All ranks must make the same sequence of render calls with the same arguments. */
+#define TRACE_COMM_ID_BYTES 128
+int trace_comm_unique_id(void* id_out /* TRACE_COMM_ID_BYTES */);
+int trace_comm_init(trace_ctx* ctx, const void* id, int rank, int world);
+int trace_comm_destroy(trace_ctx* ctx);
+int trace_comm_info(const trace_ctx* ctx, int* rank, int* world, int* nccl_version /* 0: no communicator */);
 
 int trace_scene_upload(trace_ctx* ctx, const trace_scene_desc* scene);
 

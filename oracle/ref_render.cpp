@@ -206,9 +206,18 @@ static int render_whitted_impl(const ref_scene* rs, const trace_camera* cam, con
 
 // ---------------------------------------------------------------- Halton, sampling.jl:43-76
 namespace ref {
-static const int64_t PRIMES_HEAD[] = {3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97,
-                                      101, 103, 107, 109, 113, 127, 131, 137, 139, 149, 151, 157, 163, 167, 173, 179, 181, 191, 193,
-                                      197, 199, 211, 223, 227, 229, 233, 239, 241, 251, 257, 263, 269, 271, 277, 281, 283, 293};
+// PRIMES (sampler/primes.jl): the 1023 odd primes 3 .. 8161; PRIMES[k] is the (k+1)-th prime.  Generated by a sieve.
+static std::vector<int64_t> make_primes() {
+    std::vector<char> composite(8200, 0);
+    std::vector<int64_t> out;
+    for (int i = 2; i < 8200 && out.size() < 1023; ++i) {
+        if (composite[i]) continue;
+        if (i > 2) out.push_back(i);
+        for (int j = i * i; j < 8200; j += i) composite[j] = 1;
+    }
+    return out;
+}
+static const std::vector<int64_t> PRIMES_HEAD = make_primes();
 static uint32_t reverse_bits32(uint32_t n) {
     n = (n << 16) | (n >> 16);
     n = ((n & 0x00ff00ffu) << 8) | ((n & 0xff00ff00u) >> 8);
@@ -223,7 +232,7 @@ static uint64_t reverse_bits64(uint64_t n) {
 }
 float radical_inverse(int64_t base_index, uint64_t a) {
     if (base_index == 0) return (float)((double)reverse_bits64(a) * 5.4210108624275222e-20);
-    int64_t base = PRIMES_HEAD[base_index - 1];            // PRIMES[base_index], 1-based
+    int64_t base = PRIMES_HEAD.at((size_t)base_index - 1);            // PRIMES[base_index], 1-based
     float inv_base = 1.0f / (float)base;
     uint64_t reversed = 0;
     float inv_base_n = 1.0f;

@@ -117,6 +117,30 @@ def check_scene(T, ctx, scene, camera, n, seed, label):
             # consistency: with t_max = Inf every closest hit is also an any-hit
             if tmax is None:
                 assert np.array_equal(occ, prim != 0)
+        # the warp-synchronous loop with batched leaves (option "leaf_wait") changes WHEN a lane tests a leaf's primitives,
+        # never which nodes / primitives a ray visits or in which order: same bits as the oracle
+        for slab, lw in ((2, 8), (2, 4), (0, 16), (2, 32), (2, 16), (0, 8)):
+            ctx.set_option("slab", slab)
+            ctx.set_option("leaf_wait", lw)
+            prim, t, b = ctx.intersect(o, d, tmax)
+            occ = ctx.occluded(o, d, tmax)
+            assert np.array_equal(prim, rprim), f"{label}/{name}/slab{slab}/leaf_wait{lw}: primitive ids differ"
+            assert np.array_equal(t.view(np.uint32), rt.view(np.uint32)), f"{label}/{name}/slab{slab}/leaf_wait{lw}: t differs"
+            assert np.array_equal(b.view(np.uint32), rb.view(np.uint32)), f"{label}/{name}/slab{slab}/leaf_wait{lw}: barycentrics differ"
+            assert np.array_equal(occ, rocc), f"{label}/{name}/slab{slab}/leaf_wait{lw}: any-hit differs"
+        ctx.set_option("leaf_wait", 0)
+        # the pair-node walk (option "walk" = 1: both children's boxes in the parent, far child pushed with its entry
+        # distance) visits the same primitives in the same order with the same t_max updates: same bits as the oracle
+        for slab in (0, 2):
+            ctx.set_option("slab", slab)
+            ctx.set_option("walk", 1)
+            prim, t, b = ctx.intersect(o, d, tmax)
+            occ = ctx.occluded(o, d, tmax)
+            assert np.array_equal(prim, rprim), f"{label}/{name}/slab{slab}/pair: {np.count_nonzero(prim != rprim)} primitive ids differ"
+            assert np.array_equal(t.view(np.uint32), rt.view(np.uint32)), f"{label}/{name}/slab{slab}/pair: t differs"
+            assert np.array_equal(b.view(np.uint32), rb.view(np.uint32)), f"{label}/{name}/slab{slab}/pair: barycentrics differ"
+            assert np.array_equal(occ, rocc), f"{label}/{name}/slab{slab}/pair: any-hit differs"
+        ctx.set_option("walk", 0)
         ctx.set_option("slab", 2)
     for s in summary:
         print("parity", *s)

@@ -8,6 +8,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtrace_cuda.so")
 
+ABI_VERSION = 2
+COMM_ID_BYTES = 128
 NODE_LEAF = 0xC0000000
 PRIM_TRIANGLE, PRIM_SPHERE = 0, 1
 TRI_FLIP, TRI_HAS_NORMALS = 1, 2
@@ -75,6 +77,10 @@ SIGNATURES = {
     "trace_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "trace_reset_stats": (C.c_int, [_P]),
     "trace_synchronize": (C.c_int, [_P]),
+    "trace_comm_unique_id": (C.c_int, [_P]),
+    "trace_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "trace_comm_destroy": (C.c_int, [_P]),
+    "trace_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "trace_scene_upload": (C.c_int, [_P, C.POINTER(SceneDesc)]),
     "trace_intersect": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P]),
     "trace_occluded": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
@@ -113,7 +119,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.trace_abi_version() != 1:
+        if lib.trace_abi_version() != ABI_VERSION:
             raise RuntimeError("libtrace_cuda.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -8,27 +8,35 @@
 // ------------------------------------------------------------------ kernels: batch closest-hit / any-hit queries
 // One thread per ray, persistent grid-stride loop (grid = multiple of the SM count).  Rays come as two float4 arrays
 // {o.xyz, t_max} and {d.xyz, -}; the closest-hit result is one float4 {t, original+1 (bits), b0, b1}.
-template <int SLAB, bool COUNT>
+template <int SLAB, bool COUNT, int WAIT>
 __global__ void __launch_bounds__(128, 8) k_intersect(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
                                                    long long n, float4* __restrict__ hits, unsigned long long* counters,
                                                    int* error_flag) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float4 o = ro[i], d = rd[i];
+    const int lane = threadIdx.x & 31;
+    for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x - lane); base < n; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + lane;
+        const bool valid = i < n;
+        const float4 o = valid ? ro[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = valid ? rd[i] : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         HitRecord h;
-        traverse<SLAB, false, COUNT>(sc, xyz(o), xyz(d), o.w, h, counters, error_flag);
+        traverse_any<SLAB, false, COUNT, WAIT>(sc, valid, xyz(o), xyz(d), o.w, h, counters, error_flag);
+        if (!valid) continue;
         uint32_t orig = 0;
         if (h.prim) orig = __float_as_uint(__ldg(&sc.prims[3 * (h.prim - 1) + 2]).w) + 1u;
         hits[i] = make_float4(h.prim ? h.t : o.w, __uint_as_float(orig), h.b0, h.b1);
     }
 }
-template <int SLAB, bool COUNT>
+template <int SLAB, bool COUNT, int WAIT>
 __global__ void __launch_bounds__(128, 8) k_occluded(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
                                                   long long n, uint8_t* __restrict__ out, unsigned long long* counters,
                                                   int* error_flag) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float4 o = ro[i], d = rd[i];
+    const int lane = threadIdx.x & 31;
+    for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x - lane); base < n; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + lane;
+        const bool valid = i < n;
+        const float4 o = valid ? ro[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = valid ? rd[i] : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         HitRecord h;
-        out[i] = traverse<SLAB, true, COUNT>(sc, xyz(o), xyz(d), o.w, h, counters, error_flag) ? 1 : 0;
+        const bool occ = traverse_any<SLAB, true, COUNT, WAIT>(sc, valid, xyz(o), xyz(d), o.w, h, counters, error_flag);
+        if (valid) out[i] = occ ? 1 : 0;
     }
 }
 
@@ -73,7 +81,8 @@ extern "C" void trace_destroy(trace_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     sppm_free(c);
-    DevBuf* all[] = {&c->b_nodes, &c->b_prims, &c->b_tnorm, &c->b_spheres, &c->b_materials, &c->b_lights, &c->b_counters};
+    trace_comm_destroy(c);
+    DevBuf* all[] = {&c->b_nodes, &c->b_pairs, &c->b_prims, &c->b_tnorm, &c->b_spheres, &c->b_materials, &c->b_lights, &c->b_counters};
     for (DevBuf* b : all) b->release();
     for (auto& b : c->b_query) b.release();
     for (auto& b : c->b_queue) b.release();
@@ -100,15 +109,19 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     if (!strcmp(key, "slab")) { if (v < 0 || v > 2) return c->fail("slab must be 0 (literal), 1 (textbook) or 2 (guarded)"); c->slab = (int)v; }
     else if (!strcmp(key, "batch")) { if (v < 1024) return c->fail("batch too small"); c->batch = v; }
     else if (!strcmp(key, "count_nodes")) c->count_nodes = v != 0;
-    else if (!strcmp(key, "persist")) c->persist = v != 0;
+    else if (!strcmp(key, "persist")) { if (v < 0 || v > 2) return c->fail("persist must be 0, 1 or 2"); c->persist = (int)v; }
+    else if (!strcmp(key, "film_mode")) { if (v != 0 && v != 1) return c->fail("film_mode must be 0 (whole film on rank 0) or 1 (one band per rank)"); c->film_mode = (int)v; }
+    else if (!strcmp(key, "fuse_primary")) c->fuse_primary = v != 0;
+    else if (!strcmp(key, "walk")) { if (v != 0 && v != 1) return c->fail("walk must be 0 (one node per step, the reference loop) or 1 (pair nodes)"); c->leaf_wait = v ? TR_WALK_PAIR : 0; }
+    else if (!strcmp(key, "leaf_wait")) { if (v != 0 && v != 4 && v != 8 && v != 16 && v != 32) return c->fail("leaf_wait must be 0, 4, 8, 16 or 32"); c->leaf_wait = (int)v; }
     else if (!strcmp(key, "lanes")) { if (v < 1 || v > trace_ctx::MAX_LANES) return c->fail("lanes must be in [1, 16]"); c->lanes = (int)v; }
     else if (!strcmp(key, "cap_percent")) { if (v < 100 || v > 1600) return c->fail("cap_percent must be in [100, 1600]"); c->cap_percent = (int)v; }
     else if (!strcmp(key, "time_kernels")) c->time_kernels = v != 0;
     else if (!strcmp(key, "graph")) c->graph = v != 0;
     else if (!strcmp(key, "sppm_lanes")) { if (v < 0 || v > trace_ctx::MAX_LANES / 2) return c->fail("sppm_lanes must be in [0, 8]"); c->sppm_lanes = (int)v; }
     else if (!strcmp(key, "deal")) c->deal = (int)v;
-    else if (!strcmp(key, "rank")) c->rank = (int)v;
-    else if (!strcmp(key, "world")) { if (v < 1) return c->fail("world must be >= 1"); c->world = (int)v; }
+    else if (!strcmp(key, "rank")) { if (c->comm) return c->fail("rank is fixed by trace_comm_init"); c->rank = (int)v; }
+    else if (!strcmp(key, "world")) { if (c->comm) return c->fail("world is fixed by trace_comm_init"); if (v < 1) return c->fail("world must be >= 1"); c->world = (int)v; }
     else return c->fail("unknown option '%s'", key);
     if (c->rank < 0 || c->rank >= c->world) { /* validated at render time */ }
     return 0;
@@ -220,6 +233,48 @@ extern "C" int trace_scene_upload(trace_ctx* c, const trace_scene_desc* d) {
         prims[3 * i] = A; prims[3 * i + 1] = B; prims[3 * i + 2] = C;
         tnorm[3 * i] = N0; tnorm[3 * i + 1] = N1; tnorm[3 * i + 2] = N2;
     }
+    // pair nodes (traverse.cuh): one 64-byte record per INTERIOR node holding both children's boxes and references.
+    // Preorder numbering: interior node i gets pair index = number of interior nodes before it.
+    std::vector<float4> pairs;
+    uint32_t root_ref = 0;
+    {
+        std::vector<uint32_t> pair_of((size_t)d->n_nodes, 0);
+        uint32_t n_pairs = 0;
+        for (int64_t i = 0; i < d->n_nodes; ++i) if ((d->nodes[i].meta >> 30) != 3) pair_of[i] = n_pairs++;
+        if (n_pairs >= 0x40000000u) return c->fail("scene: too many interior nodes");
+        pairs.resize((size_t)n_pairs * 4);
+        const float qnan = std::nanf("");
+        auto child_ref = [&](int64_t k) -> uint32_t {
+            const trace_bvh_node& n = d->nodes[k];
+            uint32_t m; memcpy(&m, &nodes[2 * k + 1].w, 4);
+            const uint32_t below = (m & 0x20000000u) ? 0x40000000u : 0u;
+            if ((n.meta >> 30) == 3) return 0x80000000u | below | n.offset;
+            return below | pair_of[k];
+        };
+        for (int64_t i = 0; i < d->n_nodes; ++i) {
+            const trace_bvh_node& n = d->nodes[i];
+            if ((n.meta >> 30) == 3) {
+                // mark the last primitive of the leaf (a zero-primitive leaf owns none and is never entered: its box is
+                // invalid and fails every slab test in the reference, Q16/Q17 - enforced below with a NaN box)
+                const uint32_t cnt = n.meta & 0x3FFFFFFFu;
+                if (cnt) { uint32_t t; memcpy(&t, &prims[3 * (size_t)(n.offset + cnt - 1)].w, 4); t |= 0x20000000u; memcpy(&prims[3 * (size_t)(n.offset + cnt - 1)].w, &t, 4); }
+                continue;
+            }
+            const int64_t kids[2] = {i + 1, (int64_t)n.offset};
+            float4* q = &pairs[(size_t)pair_of[i] * 4];
+            for (int k = 0; k < 2; ++k) {
+                const trace_bvh_node& ch = d->nodes[kids[k]];
+                float4 a = nodes[2 * kids[k]], b = nodes[2 * kids[k] + 1];
+                if ((ch.meta >> 30) == 3 && (ch.meta & 0x3FFFFFFFu) == 0u) { a.x = a.y = a.z = a.w = qnan; b.x = b.y = qnan; }
+                const uint32_t ref = child_ref(kids[k]);
+                const uint32_t extra = k == 0 ? (n.meta >> 30) : 0u;          // split axis of THIS node, in the first half
+                memcpy(&b.z, &ref, 4); memcpy(&b.w, &extra, 4);
+                q[2 * k] = a; q[2 * k + 1] = b;
+            }
+        }
+        if (d->n_nodes > 0) root_ref = child_ref(0) & ~0x40000000u;
+        if (d->n_nodes > 0 && (d->nodes[0].meta >> 30) == 3 && (d->nodes[0].meta & 0x3FFFFFFFu) == 0u) root_ref = 0x80000000u;   // (cannot be hit: see below)
+    }
     std::vector<DeviceSphere> spheres((size_t)d->n_spheres);
     for (int64_t i = 0; i < d->n_spheres; ++i) {
         static_assert(sizeof(DeviceSphere) == sizeof(trace_sphere), "sphere layout");
@@ -271,6 +326,7 @@ extern "C" int trace_scene_upload(trace_ctx* c, const trace_scene_desc* d) {
     };
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
     TR_CUDA(c, put(c->b_nodes, nodes.data(), nodes.size() * sizeof(float4)));
+    TR_CUDA(c, put(c->b_pairs, pairs.data(), pairs.size() * sizeof(float4)));
     TR_CUDA(c, put(c->b_prims, prims.data(), prims.size() * sizeof(float4)));
     TR_CUDA(c, put(c->b_tnorm, tnorm.data(), tnorm.size() * sizeof(float4)));
     TR_CUDA(c, put(c->b_spheres, spheres.data(), spheres.size() * sizeof(DeviceSphere)));
@@ -278,7 +334,7 @@ extern "C" int trace_scene_upload(trace_ctx* c, const trace_scene_desc* d) {
     TR_CUDA(c, put(c->b_lights, lights.data(), lights.size() * sizeof(DeviceLight)));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));      // host staging vectors die at return
     DeviceScene& s = c->scene;
-    s.nodes = c->b_nodes.as<float4>(); s.prims = c->b_prims.as<float4>(); s.tnorm = c->b_tnorm.as<float4>();
+    s.nodes = c->b_nodes.as<float4>(); s.pairs = c->b_pairs.as<float4>(); s.root_ref = root_ref; s.prims = c->b_prims.as<float4>(); s.tnorm = c->b_tnorm.as<float4>();
     s.spheres = c->b_spheres.as<DeviceSphere>(); s.materials = c->b_materials.as<DeviceMaterial>();
     s.lights = c->b_lights.as<DeviceLight>();
     s.n_nodes = (int)d->n_nodes; s.n_prims = (int)d->n_prims; s.n_spheres = (int)d->n_spheres;
@@ -330,16 +386,10 @@ static int launch_intersect(trace_ctx* c, const float4* ro, const float4* rd, in
     unsigned long long* cnt = ctx_stats64(c) + ST_NODES;
     const int grid = (int)std::min<int64_t>((n + 127) / 128, (int64_t)persistent_grid(c, 16));
     if (c->time_kernels) cudaEventRecord(c->evk0, c->stream);
-    if (c->slab == 0) {
-        if (c->count_nodes) k_intersect<0, true><<<std::min(grid, occupancy_grid(c, k_intersect<0, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
-        else k_intersect<0, false><<<std::min(grid, occupancy_grid(c, k_intersect<0, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
-    } else if (c->slab == 2) {
-        if (c->count_nodes) k_intersect<2, true><<<std::min(grid, occupancy_grid(c, k_intersect<2, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
-        else k_intersect<2, false><<<std::min(grid, occupancy_grid(c, k_intersect<2, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
-    } else {
-        if (c->count_nodes) k_intersect<1, true><<<std::min(grid, occupancy_grid(c, k_intersect<1, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
-        else k_intersect<1, false><<<std::min(grid, occupancy_grid(c, k_intersect<1, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
-    }
+    trav_dispatch(c, [&](auto S, auto C_, auto W) {
+        auto k = k_intersect<decltype(S)::value, decltype(C_)::value, decltype(W)::value>;
+        k<<<std::min(grid, occupancy_grid(c, k, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, hits, cnt, err);
+    });
     if (c->time_kernels) cudaEventRecord(c->evk1, c->stream);
     TR_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches++;
@@ -350,16 +400,10 @@ static int launch_occluded(trace_ctx* c, const float4* ro, const float4* rd, int
     unsigned long long* cnt = ctx_stats64(c) + ST_NODES;
     const int grid = (int)std::min<int64_t>((n + 127) / 128, (int64_t)persistent_grid(c, 16));
     if (c->time_kernels) cudaEventRecord(c->evk0, c->stream);
-    if (c->slab == 0) {
-        if (c->count_nodes) k_occluded<0, true><<<std::min(grid, occupancy_grid(c, k_occluded<0, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
-        else k_occluded<0, false><<<std::min(grid, occupancy_grid(c, k_occluded<0, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
-    } else if (c->slab == 2) {
-        if (c->count_nodes) k_occluded<2, true><<<std::min(grid, occupancy_grid(c, k_occluded<2, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
-        else k_occluded<2, false><<<std::min(grid, occupancy_grid(c, k_occluded<2, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
-    } else {
-        if (c->count_nodes) k_occluded<1, true><<<std::min(grid, occupancy_grid(c, k_occluded<1, true>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
-        else k_occluded<1, false><<<std::min(grid, occupancy_grid(c, k_occluded<1, false>, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
-    }
+    trav_dispatch(c, [&](auto S, auto C_, auto W) {
+        auto k = k_occluded<decltype(S)::value, decltype(C_)::value, decltype(W)::value>;
+        k<<<std::min(grid, occupancy_grid(c, k, 128)), 128, 0, c->stream>>>(c->scene, ro, rd, n, out, cnt, err);
+    });
     if (c->time_kernels) cudaEventRecord(c->evk1, c->stream);
     TR_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches++;
@@ -458,7 +502,7 @@ extern "C" int trace_render_whitted_device(trace_ctx* c, const trace_camera* cam
     cudaSetDevice(c->device);
     if (!c->have_scene) return c->fail("no scene uploaded");
     if (!cam || !film || !film_dev) return c->fail("trace_render_whitted: null argument");
-    if (spp < 1 || max_depth < 1 || max_depth > 24) return c->fail("trace_render_whitted: bad spp / max_depth");
+    if (spp < 1 || max_depth < 1 || max_depth > TR_MAX_DEPTH) return c->fail("trace_render_whitted: spp must be >= 1 and max_depth in [1, %d]", TR_MAX_DEPTH);
     return whitted_render_device(c, cam, film, spp, max_depth, seed, (float*)film_dev);
 }
 
@@ -466,20 +510,27 @@ extern "C" int trace_render_whitted(trace_ctx* c, const trace_camera* cam, const
                                     uint64_t seed, float* film_xyzw) {
     if (!c) return 1;
     cudaSetDevice(c->device);
-    if (!cam || !film || !film_xyzw) return c->fail("trace_render_whitted: null argument");
+    if (!cam || !film) return c->fail("trace_render_whitted: null argument");
     const size_t w = (size_t)(film->crop_x1 - film->crop_x0 + 1), h = (size_t)(film->crop_y1 - film->crop_y0 + 1);
-    const size_t bytes = w * h * 4 * sizeof(float);
+    // the part of the film this rank delivers (all of it on one GPU; see trace_comm_init for the multi-rank modes)
+    long long p0 = 0, p1 = 0;
+    whitted_film_range(c, (long long)(w * h), &p0, &p1);
+    if (p1 > p0 && !film_xyzw) return c->fail("trace_render_whitted: null film");
+    const size_t bytes = w * h * 4 * sizeof(float), off = (size_t)p0 * 4 * sizeof(float), part = (size_t)(p1 - p0) * 4 * sizeof(float);
     TR_CUDA(c, c->b_misc[7].ensure(bytes));
+    char* dev = c->b_misc[7].as<char>();
     // the caller's film is only needed by the final merge: upload it on the copy stream while the render runs
-    TR_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
-    TR_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
-    TR_CUDA(c, cudaMemcpyAsync(c->b_misc[7].p, film_xyzw, bytes, cudaMemcpyHostToDevice, c->copy_stream));
-    TR_CUDA(c, cudaEventRecord(c->ev_copy, c->copy_stream));
-    c->film_upload_pending = true;
-    const int rc = trace_render_whitted_device(c, cam, film, spp, max_depth, seed, c->b_misc[7].p);
+    if (part) {
+        TR_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+        TR_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+        TR_CUDA(c, cudaMemcpyAsync(dev + off, (const char*)film_xyzw + off, part, cudaMemcpyHostToDevice, c->copy_stream));
+        TR_CUDA(c, cudaEventRecord(c->ev_copy, c->copy_stream));
+        c->film_upload_pending = true;
+    }
+    const int rc = trace_render_whitted_device(c, cam, film, spp, max_depth, seed, dev);
     if (c->film_upload_pending) { cudaStreamWaitEvent(c->stream, c->ev_copy, 0); c->film_upload_pending = false; }
     if (rc) { cudaStreamSynchronize(c->stream); return 1; }
-    TR_CUDA(c, cudaMemcpyAsync(film_xyzw, c->b_misc[7].p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (part) TR_CUDA(c, cudaMemcpyAsync((char*)film_xyzw + off, dev + off, part, cudaMemcpyDeviceToHost, c->stream));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }

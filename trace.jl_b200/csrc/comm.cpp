@@ -1,0 +1,152 @@
+// comm.cpp — the library's own NCCL communicator (one rank per trace_ctx / GPU).
+//
+// the path has exactly two exchange steps - ONE sum of the private films at the end of a Whitted render
+// (reference: merge_film_tile! into the shared film, src/film.jl:182-193) and, per SPPM iteration, the all-gather of the
+// visible points and ONE all-reduce(sum) of the per-pixel (Phi, M) statistics (reference: the atomics of
+// src/integrators/sppm.jl:385-401 on shared memory).  They run inside the library on the context's stream, so a caller
+// (Julia, C, Python) needs no collective library of its own: rank 0 obtains an id with trace_comm_unique_id, hands it
+// to the other ranks by whatever means it has (threads of one process: a shared variable; processes: a file, MPI, a
+// socket), and every rank calls trace_comm_init.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy already loaded into the process if there is one - e.g.
+// the one PyTorch ships - else the system's), so libtrace_cuda.so itself has no link-time dependency on it and single-GPU
+// users never load it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "context.hpp"
+
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    if (api.handle || !api.error.empty()) return &api;
+    const char* override_path = getenv("TRACE_NCCL_LIB");
+    const char* names[] = {override_path, "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);       // the copy the process already has, if any
+        if (!api.handle) api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) { api.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found"); return &api; }
+    bool ok = true;
+    auto sym = [&](const char* name) -> void* { void* p = dlsym(api.handle, name); if (!p) { ok = false; api.error = std::string("libnccl lacks ") + name; } return p; };
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.ReduceScatter = (decltype(api.ReduceScatter))sym("ncclReduceScatter");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+    return &api;
+}
+
+int nccl_fail(trace_ctx* c, const char* what, ncclResult_t r) {
+    NcclApi* a = nccl_api();
+    return c->fail("%s failed: %s", what, a->GetErrorString ? a->GetErrorString(r) : "?");
+}
+}  // namespace
+
+#define TR_NCCL(ctx, call)                                          \
+    do {                                                            \
+        ncclResult_t r__ = (call);                                  \
+        if (r__ != ncclSuccess) return nccl_fail((ctx), #call, r__); \
+    } while (0)
+
+extern "C" int trace_comm_unique_id(void* id_out) {
+    if (!id_out) return 1;
+    NcclApi* a = nccl_api();
+    if (!a->handle) return 2;
+    static_assert(sizeof(ncclUniqueId) == TRACE_COMM_ID_BYTES, "TRACE_COMM_ID_BYTES must be NCCL's unique-id size");
+    ncclUniqueId id;
+    if (a->GetUniqueId(&id) != ncclSuccess) return 3;
+    memcpy(id_out, &id, sizeof(id));
+    return 0;
+}
+
+extern "C" int trace_comm_init(trace_ctx* c, const void* id, int rank, int world) {
+    if (!c) return 1;
+    if (!id || world < 1 || rank < 0 || rank >= world) return c->fail("trace_comm_init: bad arguments (rank %d, world %d)", rank, world);
+    NcclApi* a = nccl_api();
+    if (!a->handle) return c->fail("trace_comm_init: %s", a->error.c_str());
+    cudaSetDevice(c->device);
+    if (c->comm) { a->CommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm = nullptr;
+    TR_NCCL(c, a->CommInitRank(&comm, world, uid, rank));
+    c->comm = comm;
+    c->rank = rank;
+    c->world = world;
+    int v = 0;
+    a->GetVersion(&v);
+    c->nccl_version = v;
+    return 0;
+}
+
+extern "C" int trace_comm_destroy(trace_ctx* c) {
+    if (!c) return 1;
+    if (c->comm) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        NcclApi* a = nccl_api();
+        if (a->handle) a->CommDestroy((ncclComm_t)c->comm);
+        c->comm = nullptr;
+    }
+    c->rank = 0;
+    c->world = 1;
+    return 0;
+}
+
+extern "C" int trace_comm_info(const trace_ctx* c, int* rank, int* world, int* nccl_version) {
+    if (!c) return 1;
+    if (rank) *rank = c->rank;
+    if (world) *world = c->world;
+    if (nccl_version) *nccl_version = c->comm ? c->nccl_version : 0;
+    return 0;
+}
+
+// ---- collectives on the context's stream (float32 sums / gathers); used by whitted.cu and sppm.cu
+int comm_reduce_sum(trace_ctx* c, const float* send, float* recv, size_t count, int root) {
+    NcclApi* a = nccl_api();
+    if (!c->comm) return c->fail("no communicator: call trace_comm_init first");
+    TR_NCCL(c, a->Reduce(send, recv, count, ncclFloat, ncclSum, root, (ncclComm_t)c->comm, c->stream));
+    return 0;
+}
+int comm_reduce_scatter_sum(trace_ctx* c, const float* send, float* recv, size_t recv_count) {
+    NcclApi* a = nccl_api();
+    if (!c->comm) return c->fail("no communicator: call trace_comm_init first");
+    TR_NCCL(c, a->ReduceScatter(send, recv, recv_count, ncclFloat, ncclSum, (ncclComm_t)c->comm, c->stream));
+    return 0;
+}
+int comm_allreduce_sum(trace_ctx* c, float* buf, size_t count) {
+    NcclApi* a = nccl_api();
+    if (!c->comm) return c->fail("no communicator: call trace_comm_init first");
+    TR_NCCL(c, a->AllReduce(buf, buf, count, ncclFloat, ncclSum, (ncclComm_t)c->comm, c->stream));
+    return 0;
+}
+int comm_allgather(trace_ctx* c, const float* send, float* recv, size_t send_count) {
+    NcclApi* a = nccl_api();
+    if (!c->comm) return c->fail("no communicator: call trace_comm_init first");
+    TR_NCCL(c, a->AllGather(send, recv, send_count, ncclFloat, (ncclComm_t)c->comm, c->stream));
+    return 0;
+}

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -52,10 +53,16 @@ struct trace_ctx {
     int64_t batch = 1 << 26;      // camera samples per wavefront batch (queues: ~350 B per sample, allocated for min(batch, work))
     int count_nodes = 0;
     int cap_percent = 200;        // ray-queue capacity per bounce level, in % of the batch size
-    int persist = 0;              // persistent warps with dynamic ray fetch (measured slower on B200: kept as an option)
+    int persist = 0;              // dynamic ray fetch in the traversal kernels: 0 off, 1 bounce levels >= 2 and shadow rays, 2 all
+    int fuse_primary = 1;         // Whitted: generate + trace the camera rays in one kernel (no primary-ray queue)
+    int cur_level = 0;            // bounce level of the extend launch being enqueued (set by the integrators)
     int work_slot = 0;
+    int leaf_wait = 0;            // 0: plain traversal loop; 4/8/16/32: warp-synchronous loop with batched leaves (traverse.cuh)
     int time_kernels = 0;
     int rank = 0, world = 1;
+    void* comm = nullptr;         // ncclComm_t of this rank (comm.cpp), null until trace_comm_init
+    int nccl_version = 0;
+    int film_mode = 0;            // multi-rank Whitted film delivery: 0 = whole film summed onto rank 0, 1 = row bands (reduce-scatter)
     // CUDA graph of one Whitted render (all lanes, all batches): a render is ~20 launches per batch and the host
     // needs ~4.5 us per launch, which bounds small renders (1/8 of a frame per GPU) - replaying a captured graph does
     // not.  Keyed by every launch parameter; camera and seed live in a device block so they may change between replays
@@ -71,7 +78,7 @@ struct trace_ctx {
     // scene
     bool have_scene = false;
     DeviceScene scene{};
-    DevBuf b_nodes, b_prims, b_tnorm, b_spheres, b_materials, b_lights;
+    DevBuf b_nodes, b_pairs, b_prims, b_tnorm, b_spheres, b_materials, b_lights;
 
     // scratch
     DevBuf b_query[4];            // ray query staging
@@ -122,6 +129,7 @@ struct trace_ctx {
     }
 
     SppmState* sppm = nullptr;
+    std::map<const void*, int> occupancy_cache;   // resident CTAs per SM of each kernel on THIS device
 
     int fail(const char* fmt, ...) {
         char buf[512];
@@ -143,8 +151,10 @@ struct trace_ctx {
 // u64 device stats block layout (ctx->b_counters, after the int counters)
 enum { ST_RAYS_EXTEND = 0, ST_RAYS_SHADOW = 1, ST_NODES = 2, ST_PRIMS = 3, ST_DEPOSITS = 4, ST_COUNT = 8 };
 static const int TR_INT_COUNTERS = 128;    // ints at the start of b_counters (64..127: work counters of persistent launches)
-// int counter slots
-enum { IC_OVERFLOW = 60, IC_ERROR = 61 };
+// int counter slots: [1 .. TR_MAX_DEPTH] ray-queue length per bounce level, [32] shadow / deposit-request queue
+enum { IC_OVERFLOW = 60, IC_ERROR = 61, IC_OVERFLOW_SHADOW = 62, IC_OVERFLOW_DEPOSIT = 63 };
+// deepest path any entry point accepts (the per-level queue counters live in slots 1..31 of a lane's counter block)
+static const int TR_MAX_DEPTH = 24;
 
 // b_counters layout: [lane 0 ints][u64 stats][lane 1 ints][lane 2 ints]...
 inline size_t ctx_counter_bytes() {
@@ -168,28 +178,56 @@ inline int persistent_grid(const trace_ctx* c, int blocks_per_sm) { return c->nu
 // full wave: with a fixed 16 CTAs/SM the 69-register traversal kernels (7 resident) ran 2.29 waves, the last one 29 %
 // full (ncu: sm__warps_active 29 % of peak against a 44 % theoretical).
 #ifdef __CUDACC__
-#include <map>
 template <class K>
-inline int occupancy_grid(const trace_ctx* c, K kernel, int block_size) {
-    static std::map<const void*, int> cache;
+inline int occupancy_grid(trace_ctx* c, K kernel, int block_size) {
+    // cached per context (one context = one device, calls on a context are serialised by the caller)
     const void* key = (const void*)kernel;
-    auto it = cache.find(key);
+    auto it = c->occupancy_cache.find(key);
     int per_sm;
-    if (it != cache.end()) per_sm = it->second;
+    if (it != c->occupancy_cache.end()) per_sm = it->second;
     else {
         per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block_size, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-        cache[key] = per_sm;
+        c->occupancy_cache[key] = per_sm;
     }
     return c->num_sms * per_sm;
 }
 #endif
 
+#include <type_traits>
+// Picks the kernel instantiation for the context's (slab, count_nodes, leaf_wait): f(slab, count, wait) gets them as
+// integral constants.  Counting is only built for the plain loop (the counts do not depend on the loop shape).
+template <class F>
+static void trav_dispatch(const trace_ctx* c, F f) {
+    using std::integral_constant;
+    const int w = c->count_nodes ? 0 : c->leaf_wait;
+    if (c->count_nodes) {
+        if (c->slab == 0) f(integral_constant<int, 0>{}, integral_constant<bool, true>{}, integral_constant<int, 0>{});
+        else if (c->slab == 2) f(integral_constant<int, 2>{}, integral_constant<bool, true>{}, integral_constant<int, 0>{});
+        else f(integral_constant<int, 1>{}, integral_constant<bool, true>{}, integral_constant<int, 0>{});
+        return;
+    }
+    if (c->slab == 1) { f(integral_constant<int, 1>{}, integral_constant<bool, false>{}, integral_constant<int, 0>{}); return; }
+#define TR_WAIT_CASE(S, W) if (c->slab == S && w == W) { f(integral_constant<int, S>{}, integral_constant<bool, false>{}, integral_constant<int, W>{}); return; }
+    TR_WAIT_CASE(2, -1) TR_WAIT_CASE(0, -1)
+    TR_WAIT_CASE(2, 8) TR_WAIT_CASE(2, 16) TR_WAIT_CASE(2, 32) TR_WAIT_CASE(2, 4)
+    TR_WAIT_CASE(0, 8) TR_WAIT_CASE(0, 16)
+#undef TR_WAIT_CASE
+    if (c->slab == 0) f(integral_constant<int, 0>{}, integral_constant<bool, false>{}, integral_constant<int, 0>{});
+    else f(integral_constant<int, 2>{}, integral_constant<bool, false>{}, integral_constant<int, 0>{});
+}
+
 // implemented in api.cu
 int ctx_device_film(trace_ctx* ctx, const trace_film_desc* film, DeviceFilm* out, DevBuf* table_buf);
 void ctx_device_camera(const trace_camera* cam, DeviceCamera* out);
 int ctx_pull_stats(trace_ctx* ctx);
+// implemented in comm.cpp: float32 collectives of the context's communicator, enqueued on ctx->stream
+int comm_reduce_sum(trace_ctx* ctx, const float* send, float* recv, size_t count, int root);
+int comm_reduce_scatter_sum(trace_ctx* ctx, const float* send, float* recv, size_t recv_count);
+int comm_allreduce_sum(trace_ctx* ctx, float* buf, size_t count);
+int comm_allgather(trace_ctx* ctx, const float* send, float* recv, size_t send_count);
 // implemented in whitted.cu / sppm.cu
 int whitted_render_device(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film, int spp, int max_depth,
                           uint64_t seed, float* film_xyzw_device);
 void sppm_free(trace_ctx* ctx);
+void whitted_film_range(const trace_ctx* ctx, long long npix, long long* p0, long long* p1);

@@ -84,6 +84,8 @@ struct DeviceLight {
 };
 struct DeviceScene {
     const float4* nodes;
+    const float4* pairs;      // 4 x float4 per INTERIOR node: both children's boxes + references (traverse.cuh, pair-node walk)
+    uint32_t root_ref;        // reference of the root: pair index 0, or TR_REF_LEAF | 0 when the tree is a single leaf
     const float4* prims;
     const float4* tnorm;
     const DeviceSphere* spheres;

@@ -74,7 +74,7 @@ __device__ __forceinline__ Interaction build_interaction(const DeviceScene& sc, 
         }
         it.ng = ng; it.ns = ns;
     } else {
-        const DeviceSphere& sp = sc.spheres[tag & 0x3FFFFFFFu];
+        const DeviceSphere& sp = sc.spheres[tag & TR_PRIM_INDEX_MASK];
         SphereHitInfo sh;
         sphere_test(sp, ray_o, ray_d, TR_INF, sh);          // same root as the accepted candidate (pure function of the ray)
         const float3 hp = sh.p;
@@ -496,13 +496,25 @@ __device__ __forceinline__ void generate_camera_ray(const DeviceCamera& c, float
 }
 
 // ------------------------------------------------------------------ Halton, sampler/sampling.jl:43-76
-__constant__ int c_primes[64] = {3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97,
-                                 101, 103, 107, 109, 113, 127, 131, 137, 139, 149, 151, 157, 163, 167, 173, 179, 181, 191, 193,
-                                 197, 199, 211, 223, 227, 229, 233, 239, 241, 251, 257, 263, 269, 271, 277, 281, 283, 293, 307,
-                                 311, 313};
+// PRIMES of the reference (sampler/primes.jl): the 1023 odd primes 3 .. 8161, i.e. Halton dimension k >= 1 uses the
+// (k+1)-th prime.  Generated at compile time (sieve), not transcribed.
+struct PrimeTable {
+    int v[1023];
+    constexpr PrimeTable() : v{} {
+        bool composite[8200] = {};
+        int n = 0;
+        for (int i = 2; i < 8200 && n < 1023; ++i) {
+            if (composite[i]) continue;
+            if (i > 2) v[n++] = i;
+            for (int j = i * i; j < 8200; j += i) composite[j] = true;
+        }
+    }
+};
+__constant__ PrimeTable c_primes = PrimeTable();
+#define TR_MAX_HALTON_DIM 1023
 __device__ __forceinline__ float radical_inverse(int base_index, unsigned long long a) {
     if (base_index == 0) return (float)((double)__brevll(a) * 5.4210108624275222e-20);
-    const unsigned long long base = (unsigned long long)c_primes[base_index - 1];
+    const unsigned long long base = (unsigned long long)c_primes.v[min(base_index, TR_MAX_HALTON_DIM) - 1];
     const float inv_base = 1.0f / (float)base;
     unsigned long long reversed = 0;
     float inv_base_n = 1.0f;

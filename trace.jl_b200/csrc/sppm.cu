@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level)
                     const float3 contrib = ((f * Li) / 1.0f) / light_pdf;
                     const float3 sdir = lpos - it.p;
                     const int q = queue_claim(&L.counters[32]);
-                    if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW] = 1; continue; }
+                    if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW_SHADOW] = 1; continue; }
                     L.so[q] = f4(it.p + 1e-6f * sdir, TR_INF);
                     L.sd[q] = f4(sdir, __int_as_float(slot));
                     L.sc_contrib[q] = f4(contrib, 0.0f);
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
             // photon landed at depth > 1: queue a deposit request for k_photon_deposit (sppm.jl:377-403).  The grid is
             // NOT consulted here - it is being rebuilt by the concurrent camera pass; the deposit kernel does the lookup
             const int q = queue_claim(&L.counters[32]);
-            if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW] = 1; continue; }
+            if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW_DEPOSIT] = 1; continue; }
             L.so[q] = f4(it.p, 0.0f);
             L.sd[q] = f4(wo, 0.0f);
             L.sc_contrib[q] = f4(beta, 0.0f);
@@ -541,7 +541,7 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     cudaSetDevice(c->device);
     if (!c->have_scene) return c->fail("no scene uploaded");
     if (!cam || !film) return c->fail("trace_sppm_begin: null argument");
-    if (max_depth < 1 || max_depth > 28) return c->fail("trace_sppm_begin: bad max_depth");
+    if (max_depth < 1 || max_depth > TR_MAX_DEPTH) return c->fail("trace_sppm_begin: max_depth must be in [1, %d]", TR_MAX_DEPTH);
     if (!(r0 > 0.0f)) return c->fail("trace_sppm_begin: bad radius");
     if (c->scene.n_lights < 1) return c->fail("trace_sppm_begin: the scene has no lights");
     sppm_free(c);
@@ -651,11 +651,14 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
 
 static int check_flags(trace_ctx* c, const char* what) {
     int* ic = ctx_icounters(c);
-    TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ic + IC_OVERFLOW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(c, cudaMemcpyAsync(c->h_flags, ic + IC_OVERFLOW, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
     c->kev_collect();
-    if (c->h_flags[1]) { cudaMemsetAsync(ic + IC_ERROR, 0, sizeof(int), c->stream); return c->fail("%s: traversal stack overflow (> 64 pending nodes)", what); }
-    if (c->h_flags[0]) { cudaMemsetAsync(ic + IC_OVERFLOW, 0, sizeof(int), c->stream); return c->fail("%s: SPPM grid item capacity exceeded", what); }
+    if (c->h_flags[0] | c->h_flags[1] | c->h_flags[2] | c->h_flags[3]) cudaMemsetAsync(ic + IC_OVERFLOW, 0, 4 * sizeof(int), c->stream);
+    if (c->h_flags[1]) return c->fail("%s: traversal stack overflow (> 64 pending nodes)", what);
+    if (c->h_flags[0]) return c->fail("%s: SPPM grid item capacity exceeded (more than 28 grid cells per visible point on average)", what);
+    if (c->h_flags[2]) return c->fail("%s: SPPM shadow-ray queue overflow (direct-lighting samples of the camera pass were dropped)", what);
+    if (c->h_flags[3]) return c->fail("%s: SPPM deposit-request queue overflow (photon deposits were dropped)", what);
     return 0;
 }
 
@@ -680,6 +683,7 @@ static int sppm_camera_lane(trace_ctx* c, SppmState* s, int l, int iteration) {
     c->stats.kernel_launches++;
     for (int level = 1; level <= W.max_depth; ++level) {
         const int cur = (level - 1) & 1;
+        c->cur_level = level;
         launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
                       stats + ST_NODES, W.flags + IC_ERROR);
         k_sppm_cam_shade<<<occupancy_grid(c, k_sppm_cam_shade, 128), 128, 0, st>>>(W, level);
@@ -759,6 +763,7 @@ static int sppm_trace_lane(trace_ctx* c, SppmState* s, int j, int iteration, int
     c->stats.kernel_launches++;
     for (int level = 1; level <= W.max_depth; ++level) {
         const int cur = (level - 1) & 1;
+        c->cur_level = level;
         launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
                       stats + ST_NODES, W.flags + IC_ERROR);
         k_photon_shade<<<occupancy_grid(c, k_photon_shade, 128), 128, 0, st>>>(W, level);

@@ -178,7 +178,13 @@ static __device__ __noinline__ bool sphere_test(const DeviceSphere& s, float3 ro
 
 #define TR_PRIM_SPHERE_BIT 0x80000000u
 #define TR_PRIM_DEGENERATE_BIT 0x40000000u
+#define TR_PRIM_LAST_BIT 0x20000000u        // last primitive of its BVH leaf (set at upload; used by the pair-node walk)
+#define TR_PRIM_INDEX_MASK 0x1FFFFFFFu
 #define TR_STACK_SIZE 64
+#define TR_WALK_PAIR (-1)     // "walk" selector of the kernels: 0 reference loop, -1 pair nodes, 4..32 batched leaves
+#ifndef TR_PARK_MAX
+#define TR_PARK_MAX 12      // a leaf slot opens as soon as this many lanes of the warp are parked on a leaf
+#endif
 
 struct HitRecord {
     uint32_t prim;      // BVH-ordered primitive index + 1, 0 = miss
@@ -218,7 +224,7 @@ __device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3
                     const float4 a = __ldg(&sc.prims[3 * pi]);
                     const uint32_t tag = __float_as_uint(a.w);
                     if (COUNT) n_prims++;
-                    if (tag == 0u) {
+                    if ((tag & ~TR_PRIM_LAST_BIT) == 0u) {
                         const float4 b = __ldg(&sc.prims[3 * pi + 1]);
                         const float4 c = __ldg(&sc.prims[3 * pi + 2]);
                         float t, b0, b1, b2;
@@ -229,7 +235,7 @@ __device__ __forceinline__ bool traverse(const DeviceScene& sc, float3 o, float3
                         }
                     } else if (tag & TR_PRIM_SPHERE_BIT) {
                         SphereHitInfo sh;
-                        if (sphere_test(sc.spheres[tag & 0x3FFFFFFFu], r.o, r.d, tmax, sh)) {
+                        if (sphere_test(sc.spheres[tag & TR_PRIM_INDEX_MASK], r.o, r.d, tmax, sh)) {
                             if (ANY) { found = true; goto done; }
                             tmax = sh.t; found = true;
                             out.prim = pi + 1; out.t = sh.t; out.b0 = 0.0f; out.b1 = 0.0f;
@@ -259,14 +265,261 @@ done:
     return found;
 }
 
+// ------------------------------------------------------------------ pair-node traversal
+// The reference walk (traverse<>() above) fetches and box-tests ONE node per iteration; every far child is pushed
+// untested and most of them fail their test when popped.  ncu (profiles/r2_extend_source_base.txt): per iteration ~98
+// instructions, 23-27 % of them stack push / pop bookkeeping at 13-19 of 32 lanes, and a dependent 32-byte fetch for every
+// tested node.  The pair layout stores, in every interior node, the boxes of its TWO children (64 bytes, 4 x 128-bit
+// loads issued together), so one fetch serves both box tests, which are independent and overlap in the pipeline:
+//   * the near child (sign of d[split_axis], as the reference) is entered right away when its test passes;
+//   * the far child's test is split: every condition of the reference's test but one is independent of t_max and is
+//     evaluated NOW - a far child failing those is never pushed, it would fail when popped as well; one passing them
+//     is pushed together with its entry distance tx_min, and the t_max-dependent condition (tx_min < t_max,
+//     bounds.jl:199) is evaluated with the t_max of the moment it is popped, which is when the reference tests it -
+//     a register compare, no fetch.
+// The set of nodes whose primitives are tested, their order, and every t_max update are exactly those of the
+// reference walk, so hits, tie-breaks and t are bit-identical (tests/test_gpu_parity.py runs both walks against the
+// oracle).  Leaves need no node of their own: a child reference is either a pair index or the offset of the leaf's first
+// primitive, and the primitive records carry a "last of its leaf" bit.  Stack: entries {ref, tx_min}, top of stack in
+// registers so a pop never waits for local memory; it holds only box-hit nodes, so it is never deeper than the
+// reference's (which overflows - BoundsError - beyond 64 pending nodes, bvh.jl:222; here that is reported as an error
+// only if 64 box-HIT nodes are pending).
+#define TR_REF_LEAF 0x80000000u
+#define TR_REF_SPHERE_BELOW 0x40000000u
+#define TR_REF_INDEX_MASK 0x3FFFFFFFu
+
+// One child's box test WITHOUT its t_max condition: the reference's verdict (SLAB 0) or reference AND conservative
+// guard (SLAB 2) for the ray (0, inf); tx_min_out is the reference's entry distance - the node is entered iff this
+// returns true and tx_min_out < t_max (bounds.jl:199) with the t_max of the moment the reference would test it.
+// Branch-free on purpose: the two children of a pair are tested back to back and their instruction streams interleave.
+template <int SLAB>
+__device__ __forceinline__ bool slab_child(const float4 n0, const float4 n1, const RayPrep& r, float& tx_min_out) {
+    const float ax0 = ((r.nx ? n0.w : n0.x) - r.o.x) * r.inv.x;
+    const float ax1 = ((r.nx ? n0.x : n0.w) - r.o.x) * r.inv.x;
+    const float ay0 = ((r.ny ? n1.x : n0.y) - r.o.y) * r.inv.y;
+    const float ay1 = ((r.ny ? n0.y : n1.x) - r.o.y) * r.inv.y;
+    const float az0 = ((r.nz ? n1.y : n0.z) - r.o.z) * r.inv.z;
+    const float az1 = ((r.nz ? n0.z : n1.y) - r.o.z) * r.inv.z;
+    bool ok = true;
+    if (SLAB == 2) {
+        // conservative interval test (NaN-transparent); its t_max part is implied by the reference's tx_min < t_max
+        const float t_enter = fmaxf(fmaxf(ax0 - r.mx, ay0 - r.my), az0 - r.mz);
+        const float t_exit = fminf(fminf(ax1 + r.mx, ay1 + r.my), az1 + r.mz);
+        const bool guard_miss = (t_enter > t_exit) | (t_exit < 0.0f);
+        ok = !guard_miss | ((__float_as_uint(n1.z) & TR_REF_SPHERE_BELOW) != 0u);
+    }
+    // bounds.jl:180-200, literally (Q26: the y far bound keeps the LARGER value), all compares false on NaN
+    ok &= !((ax0 > ay1) | (ay0 > ax1));
+    float tx_min = ay0 > ax0 ? ay0 : ax0;
+    float tx_max = ay1 > ax1 ? ay1 : ax1;
+    ok &= !((tx_min > az1) | (az0 > tx_max));
+    tx_min = az0 > tx_min ? az0 : tx_min;
+    tx_max = az1 < tx_max ? az1 : tx_max;
+    ok &= tx_max > 0.0f;
+    tx_min_out = tx_min;
+    return ok;               // the caller adds the one t_max-dependent condition: tx_min < t_max
+}
+
+template <int SLAB, bool ANY, bool COUNT>
+__device__ __forceinline__ bool traverse_pair(const DeviceScene& sc, float3 o, float3 d, float tmax, HitRecord& out,
+                                              unsigned long long* counters, int* error_flag) {
+    out.prim = 0; out.t = tmax; out.b0 = 0.0f; out.b1 = 0.0f;
+    if (sc.n_nodes == 0) return false;
+    const RayPrep r = prepare_ray(o, d, sc.scene_scale);
+    unsigned n_nodes = 1, n_prims = 0;
+    bool found = false;
+    uint32_t item;
+    {   // the root's own box (bvh.jl:224): the one node that is not somebody's child
+        const float4 n0 = __ldg(&sc.nodes[0]), n1 = __ldg(&sc.nodes[1]);
+        if (!slab_test<SLAB>(n0, n1, r, tmax)) { item = 0; goto done; }
+        item = sc.root_ref;
+    }
+    {
+    uint2 stack[TR_STACK_SIZE];
+    uint2 tos = make_uint2(0u, 0u);
+    int sp = 0;
+    const unsigned signs = (r.nx ? 1u : 0u) | (r.ny ? 2u : 0u) | (r.nz ? 4u : 0u);
+    const bool cull_far = sc.n_spheres == 0;
+    for (;;) {
+        if (item & TR_REF_LEAF) {
+            uint32_t pi = item & TR_REF_INDEX_MASK;
+            for (;; ++pi) {
+                const float4 a = __ldg(&sc.prims[3 * pi]);
+                const uint32_t tag = __float_as_uint(a.w);
+                if (COUNT) n_prims++;
+                if ((tag & ~TR_PRIM_LAST_BIT) == 0u) {
+                    const float4 b = __ldg(&sc.prims[3 * pi + 1]);
+                    const float4 c = __ldg(&sc.prims[3 * pi + 2]);
+                    float t, b0, b1, b2;
+                    if (triangle_test(a, b, c, r, tmax, t, b0, b1, b2)) {
+                        found = true;
+                        if (ANY) goto done;
+                        tmax = t;
+                        out.prim = pi + 1; out.t = t; out.b0 = b0; out.b1 = b1;
+                    }
+                } else if (tag & TR_PRIM_SPHERE_BIT) {
+                    SphereHitInfo sh;
+                    if (sphere_test(sc.spheres[tag & TR_PRIM_INDEX_MASK], r.o, r.d, tmax, sh)) {
+                        found = true;
+                        if (ANY) goto done;
+                        tmax = sh.t;
+                        out.prim = pi + 1; out.t = sh.t; out.b0 = 0.0f; out.b1 = 0.0f;
+                    }
+                }
+                if (tag & TR_PRIM_LAST_BIT) break;
+            }
+        } else {
+            const float4* np = sc.pairs + 4u * (item & TR_REF_INDEX_MASK);
+            const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+            if (COUNT) n_nodes += 2;
+            float t0, t1;
+            const bool s0 = slab_child<SLAB>(q0, q1, r, t0);
+            const bool s1 = slab_child<SLAB>(q2, q3, r, t1);
+            const bool neg = (signs >> (__float_as_uint(q1.w) & 3u)) & 1u;      // near child = second child iff d[axis] < 0
+            const uint32_t ref0 = __float_as_uint(q1.z), ref1 = __float_as_uint(q3.z);
+            const float near_t = neg ? t1 : t0, far_t = neg ? t0 : t1;
+            const bool near_hit = (neg ? s1 : s0) & (near_t < tmax);               // tested now, as the reference does
+            const bool far_static = neg ? s0 : s1;                                // tested when popped: t_max may differ
+            const uint32_t near_ref = neg ? ref1 : ref0, far_ref = neg ? ref0 : ref1;
+            if (near_hit) {
+                item = near_ref;
+                // Early cull of the far child: a triangle hit never raises t_max by more than rounding (t = ts / det
+                // with ts <= t_max * det: 3 roundings), so a far child beyond t_max (1 + 1e-3) can never pass when
+                // popped.  An analytic sphere CAN raise t_max (Q12: from inside, the far root is reported without
+                // re-checking t_max, sphere.jl:137-149), so scenes with spheres keep every statically hit far child.
+                if (far_static & (cull_far ? !(far_t > tmax + fabsf(tmax) * 1e-3f) : true)) {
+                    if (sp >= TR_STACK_SIZE) { if (error_flag) *error_flag = 1; goto done; }
+                    stack[sp++] = tos;
+                    tos = make_uint2(far_ref, __float_as_uint(far_t));
+                }
+                continue;
+            }
+            const bool far_hit = far_static & (far_t < tmax);
+            if (far_hit) { item = far_ref; continue; }
+        }
+        // pop the next pending node that the (shrunken) t_max still lets in
+        for (;;) {
+            if (sp == 0) goto done;
+            item = tos.x;
+            const float t_in = __uint_as_float(tos.y);
+            tos = stack[--sp];
+            if (t_in < tmax) break;
+        }
+    }
+    }
+done:
+    if (COUNT && counters) { atomicAdd(&counters[0], (unsigned long long)n_nodes); atomicAdd(&counters[1], (unsigned long long)n_prims); }
+    return found;
+}
+
+// ------------------------------------------------------------------ warp-synchronous traversal with batched leaves
+// Same walk, same order, same tests as traverse<>() per ray - only WHEN a lane runs the primitive tests of a leaf changes.
+// In the plain loop a warp executes the ~120-instruction triangle test whenever ANY of its lanes stands on a leaf;
+// leaves are ~2 % of the node visits, so with 32 lanes about every second iteration pays for it with one or two lanes
+// active (ncu round 1: 21 of 32 lanes on coherent primary rays, 12-15 on secondary rays).  Here the warp iterates in
+// explicit lock step (one vote per iteration); a lane that reaches a leaf PARKS - it keeps the leaf pending and
+// idles - until the warp opens a leaf slot: every WAIT-th iteration, or as soon as PARK_MAX lanes are parked, or when
+// no lane is left traversing.  All parked lanes then run the primitive tests together.  A ray visits only ~1.6
+// leaves, so parking adds a few idle iterations to a ~77-iteration walk, while the primitive tests run far less often
+// and with many lanes.  Per-ray results are those of traverse<>(): node sequence, t_max updates and tie-breaks are
+// unchanged (each lane still walks its own ray strictly in order).
+// All 32 lanes of the warp must call this together; `valid == false` lanes only take part in the votes.
+template <int SLAB, bool ANY, bool COUNT, int WAIT, int PARK_MAX>
+__device__ __forceinline__ bool traverse_lb(const DeviceScene& sc, bool valid, float3 o, float3 d, float tmax, HitRecord& out,
+                                            unsigned long long* counters, int* error_flag) {
+    const unsigned full = 0xffffffffu;
+    out.prim = 0; out.t = tmax; out.b0 = 0.0f; out.b1 = 0.0f;
+    const RayPrep r = prepare_ray(o, d, sc.scene_scale);
+    uint32_t stack[TR_STACK_SIZE];
+    int sp = 0;
+    uint32_t cur = 0;
+    uint32_t leaf_off = 0, leaf_cnt = 0;          // pending leaf of this lane (leaf_cnt > 0: parked)
+    unsigned n_nodes = 0, n_prims = 0;
+    bool found = false;
+    bool done = !valid || sc.n_nodes == 0;
+    for (uint32_t it = 1;; ++it) {
+        const unsigned m_trav = __ballot_sync(full, !done && leaf_cnt == 0u);
+        const unsigned m_park = __ballot_sync(full, leaf_cnt != 0u);
+        if ((m_trav | m_park) == 0u) break;
+        const bool leaf_slot = m_trav == 0u || __popc(m_park) >= PARK_MAX || (it & (uint32_t)(WAIT - 1)) == 0u;
+        if (leaf_cnt) {
+            if (!leaf_slot) continue;                 // parked
+            for (uint32_t i = 0; i < leaf_cnt; ++i) {
+                const uint32_t pi = leaf_off + i;
+                const float4 a = __ldg(&sc.prims[3 * pi]);
+                const uint32_t tag = __float_as_uint(a.w);
+                if (COUNT) n_prims++;
+                if ((tag & ~TR_PRIM_LAST_BIT) == 0u) {
+                    const float4 b = __ldg(&sc.prims[3 * pi + 1]);
+                    const float4 c = __ldg(&sc.prims[3 * pi + 2]);
+                    float t, b0, b1, b2;
+                    if (triangle_test(a, b, c, r, tmax, t, b0, b1, b2)) {
+                        found = true;
+                        if (ANY) { done = true; break; }
+                        tmax = t;
+                        out.prim = pi + 1; out.t = t; out.b0 = b0; out.b1 = b1;
+                    }
+                } else if (tag & TR_PRIM_SPHERE_BIT) {
+                    SphereHitInfo sh;
+                    if (sphere_test(sc.spheres[tag & TR_PRIM_INDEX_MASK], r.o, r.d, tmax, sh)) {
+                        found = true;
+                        if (ANY) { done = true; break; }
+                        tmax = sh.t;
+                        out.prim = pi + 1; out.t = sh.t; out.b0 = 0.0f; out.b1 = 0.0f;
+                    }
+                }
+            }
+            leaf_cnt = 0;
+            if (!done) { if (sp == 0) done = true; else cur = stack[--sp]; }
+            continue;
+        }
+        if (done) continue;
+        const float4 n0 = __ldg(&sc.nodes[2 * cur]);
+        const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
+        if (COUNT) n_nodes++;
+        if (slab_test<SLAB>(n0, n1, r, tmax)) {
+            const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
+            if ((meta >> 30) == 3u) {
+                leaf_cnt = meta & TR_NODE_COUNT_MASK;
+                leaf_off = offset;
+                if (leaf_cnt) continue;
+            } else {
+                const uint32_t axis = meta >> 30;
+                const bool neg = axis == 0 ? r.nx : (axis == 1 ? r.ny : r.nz);
+                if (sp >= TR_STACK_SIZE) { if (error_flag) *error_flag = 1; done = true; continue; }
+                if (neg) { stack[sp++] = cur + 1; cur = offset; }
+                else     { stack[sp++] = offset; cur = cur + 1; }
+                continue;
+            }
+        }
+        if (sp == 0) done = true; else cur = stack[--sp];
+    }
+    if (COUNT && counters && valid) { atomicAdd(&counters[0], (unsigned long long)n_nodes); atomicAdd(&counters[1], (unsigned long long)n_prims); }
+    return found;
+}
+
+// dispatch: WAIT == 0 is the plain per-thread loop.  All 32 lanes of a warp must call this together.
+template <int SLAB, bool ANY, bool COUNT, int WAIT>
+__device__ __forceinline__ bool traverse_any(const DeviceScene& sc, bool valid, float3 o, float3 d, float tmax, HitRecord& out,
+                                             unsigned long long* counters, int* error_flag) {
+    if (WAIT == 0 || WAIT == TR_WALK_PAIR) {
+        if (!valid) { out.prim = 0; out.t = tmax; out.b0 = 0.0f; out.b1 = 0.0f; return false; }
+        if (WAIT == TR_WALK_PAIR) return traverse_pair<SLAB == 1 ? 0 : SLAB, ANY, COUNT>(sc, o, d, tmax, out, counters, error_flag);
+        return traverse<SLAB, ANY, COUNT>(sc, o, d, tmax, out, counters, error_flag);
+    } else return traverse_lb<SLAB, ANY, COUNT, (WAIT > 0 ? WAIT : 1), TR_PARK_MAX>(sc, valid, o, d, tmax, out, counters, error_flag);
+}
+
 // ------------------------------------------------------------------ persistent warps with dynamic ray fetch
 // The plain kernels give each thread a fixed slice of the queue; a warp then runs until its SLOWEST ray is done
-// (ncu: 20 of 32 lanes active on average for primary rays, 13-17 for secondary / shadow rays).  Here a warp keeps
-// traversing and, whenever at least TR_REFILL_LANES lanes have finished, those lanes claim the next rays of the queue
-// from a device-side counter (one warp-aggregated atomic) - the "persistent threads + dynamic fetch" scheme of
-// Aila & Laine.  Each lane runs exactly the loop of traverse<>() on its ray, one node per iteration, so per-ray
-// results are unchanged.
-#define TR_REFILL_LANES 8
+// (ncu, pair walk: 28 of 32 lanes enter the box tests on coherent primary rays, but only 23 / 19 on the rays of bounce
+// levels 2 / 3 and 23 on shadow rays).  Here a warp keeps walking and, whenever at least TR_REFILL_LANES of its lanes
+// are idle, those lanes claim the next rays of the queue from a device-side counter (one warp-aggregated atomic) -
+// the "persistent threads + dynamic fetch" scheme of Aila & Laine.  Each lane runs exactly the steps of
+// traverse_pair<>() on its ray, so per-ray results are unchanged.  Used for the incoherent launches (bounce levels
+// >= 2, shadow rays), where the tails are long and there is little coherence to lose by mixing rays in a warp.
+#ifndef TR_REFILL_LANES
+#define TR_REFILL_LANES 12
+#endif
 
 template <int SLAB, bool ANY, class Finish>
 __device__ __forceinline__ void trace_persistent(const DeviceScene& sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
@@ -278,73 +531,93 @@ __device__ __forceinline__ void trace_persistent(const DeviceScene& sc, const fl
     int ray = 0;
     RayPrep r;
     float tmax = 0.0f;
-    uint32_t cur = 0;
+    uint32_t item = 0;
     int sp = 0;
-    uint32_t stack[TR_STACK_SIZE];
+    uint2 tos = make_uint2(0u, 0u);
+    uint2 stack[TR_STACK_SIZE];
+    unsigned signs = 0;
     HitRecord out;
     out.prim = 0; out.t = 0.0f; out.b0 = 0.0f; out.b1 = 0.0f;
+    const bool cull_far = sc.n_spheres == 0;
     if (sc.n_nodes == 0) n = 0;
     for (;;) {
         const unsigned idle = __ballot_sync(full, !have);
-        if (idle != 0u && !exhausted && (__popc(idle) >= TR_REFILL_LANES || idle == full)) {
-            int base = 0;
-            const int want = __popc(idle);
-            if (lane == (unsigned)(__ffs(idle) - 1)) base = atomicAdd(work_counter, want);
-            base = __shfl_sync(full, base, __ffs(idle) - 1);
-            if (base + want >= n) exhausted = true;
-            const int mine = base + __popc(idle & lt_mask);
-            if (!have && mine < n) {
-                const float4 o4 = ro[mine], d4 = rd[mine];
-                r = prepare_ray(xyz(o4), xyz(d4), sc.scene_scale);
-                tmax = o4.w; ray = mine; cur = 0; sp = 0; have = true;
-                out.prim = 0; out.t = tmax; out.b0 = 0.0f; out.b1 = 0.0f;
+        if (idle != 0u) {
+            if (!exhausted && (__popc(idle) >= TR_REFILL_LANES || idle == full)) {
+                int base = 0;
+                const int want = __popc(idle);
+                const int leader = __ffs(idle) - 1;
+                if ((int)lane == leader) base = atomicAdd(work_counter, want);
+                base = __shfl_sync(full, base, leader);
+                if (base + want >= n) exhausted = true;
+                const int mine = base + __popc(idle & lt_mask);
+                if (!have && mine < n) {
+                    const float4 o4 = ro[mine], d4 = rd[mine];
+                    r = prepare_ray(xyz(o4), xyz(d4), sc.scene_scale);
+                    tmax = o4.w; ray = mine; sp = 0;
+                    out.prim = 0; out.t = tmax; out.b0 = 0.0f; out.b1 = 0.0f;
+                    signs = (r.nx ? 1u : 0u) | (r.ny ? 2u : 0u) | (r.nz ? 4u : 0u);
+                    const float4 n0 = __ldg(&sc.nodes[0]), n1 = __ldg(&sc.nodes[1]);
+                    if (slab_test<SLAB>(n0, n1, r, tmax)) { item = sc.root_ref; have = true; }
+                    else finish(ray, out);                           // misses the root box: done at once
+                }
+                continue;
             }
+            if (idle == full) break;                                 // queue exhausted and every lane finished
         }
-        if (__ballot_sync(full, have) == 0u) { if (exhausted) break; else continue; }
         if (have) {
-            const float4 n0 = __ldg(&sc.nodes[2 * cur]);
-            const float4 n1 = __ldg(&sc.nodes[2 * cur + 1]);
-            bool descend = false, done = false;
-            if (slab_test<SLAB>(n0, n1, r, tmax)) {
-                const uint32_t offset = __float_as_uint(n1.z), meta = __float_as_uint(n1.w);
-                if ((meta >> 30) == 3u) {
-                    const uint32_t count = meta & TR_NODE_COUNT_MASK;
-                    for (uint32_t i = 0; i < count; ++i) {
-                        const uint32_t pi = offset + i;
-                        const float4 a = __ldg(&sc.prims[3 * pi]);
-                        const uint32_t tag = __float_as_uint(a.w);
-                        if (tag == 0u) {
-                            const float4 b = __ldg(&sc.prims[3 * pi + 1]);
-                            const float4 c = __ldg(&sc.prims[3 * pi + 2]);
-                            float t, b0, b1, b2;
-                            if (triangle_test(a, b, c, r, tmax, t, b0, b1, b2)) {
-                                out.prim = pi + 1;
-                                if (ANY) { done = true; break; }
-                                tmax = t; out.t = t; out.b0 = b0; out.b1 = b1;
-                            }
-                        } else if (tag & TR_PRIM_SPHERE_BIT) {
-                            SphereHitInfo sh;
-                            if (sphere_test(sc.spheres[tag & 0x3FFFFFFFu], r.o, r.d, tmax, sh)) {
-                                out.prim = pi + 1;
-                                if (ANY) { done = true; break; }
-                                tmax = sh.t; out.t = sh.t; out.b0 = 0.0f; out.b1 = 0.0f;
-                            }
+            bool done = false;
+            if (item & TR_REF_LEAF) {
+                uint32_t pi = item & TR_REF_INDEX_MASK;
+                for (;; ++pi) {
+                    const float4 a = __ldg(&sc.prims[3 * pi]);
+                    const uint32_t tag = __float_as_uint(a.w);
+                    if ((tag & ~TR_PRIM_LAST_BIT) == 0u) {
+                        const float4 b = __ldg(&sc.prims[3 * pi + 1]);
+                        const float4 c = __ldg(&sc.prims[3 * pi + 2]);
+                        float t, b0, b1, b2;
+                        if (triangle_test(a, b, c, r, tmax, t, b0, b1, b2)) {
+                            out.prim = pi + 1;
+                            if (ANY) { done = true; break; }
+                            tmax = t; out.t = t; out.b0 = b0; out.b1 = b1;
+                        }
+                    } else if (tag & TR_PRIM_SPHERE_BIT) {
+                        SphereHitInfo sh;
+                        if (sphere_test(sc.spheres[tag & TR_PRIM_INDEX_MASK], r.o, r.d, tmax, sh)) {
+                            out.prim = pi + 1;
+                            if (ANY) { done = true; break; }
+                            tmax = sh.t; out.t = sh.t; out.b0 = 0.0f; out.b1 = 0.0f;
                         }
                     }
-                } else {
-                    const uint32_t axis = meta >> 30;
-                    const bool neg = axis == 0 ? r.nx : (axis == 1 ? r.ny : r.nz);
-                    if (sp >= TR_STACK_SIZE) { if (error_flag) *error_flag = 1; done = true; }
-                    else {
-                        if (neg) { stack[sp++] = cur + 1; cur = offset; }
-                        else     { stack[sp++] = offset; cur = cur + 1; }
-                        descend = true;
-                    }
+                    if (tag & TR_PRIM_LAST_BIT) break;
                 }
+            } else {
+                const float4* np = sc.pairs + 4u * (item & TR_REF_INDEX_MASK);
+                const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+                float t0, t1;
+                const bool s0 = slab_child<SLAB>(q0, q1, r, t0);
+                const bool s1 = slab_child<SLAB>(q2, q3, r, t1);
+                const bool neg = (signs >> (__float_as_uint(q1.w) & 3u)) & 1u;
+                const uint32_t ref0 = __float_as_uint(q1.z), ref1 = __float_as_uint(q3.z);
+                const float near_t = neg ? t1 : t0, far_t = neg ? t0 : t1;
+                const bool near_hit = (neg ? s1 : s0) & (near_t < tmax);
+                const bool far_static = neg ? s0 : s1;
+                const uint32_t near_ref = neg ? ref1 : ref0, far_ref = neg ? ref0 : ref1;
+                if (near_hit) {
+                    item = near_ref;
+                    if (far_static & (cull_far ? !(far_t > tmax + fabsf(tmax) * 1e-3f) : true)) {
+                        if (sp >= TR_STACK_SIZE) { if (error_flag) *error_flag = 1; done = true; }
+                        else { stack[sp++] = tos; tos = make_uint2(far_ref, __float_as_uint(far_t)); }
+                    }
+                    if (!done) continue;
+                } else if (far_static & (far_t < tmax)) { item = far_ref; continue; }
             }
-            if (!descend && !done) {
-                if (sp == 0) done = true;
-                else cur = stack[--sp];
+            while (!done) {                                          // pop the next pending node t_max still lets in
+                if (sp == 0) { done = true; break; }
+                item = tos.x;
+                const float t_in = __uint_as_float(tos.y);
+                tos = stack[--sp];
+                if (t_in < tmax) break;
             }
             if (done) { finish(ray, out); have = false; }
         }

@@ -12,29 +12,38 @@
 #ifndef TR_TRAV_MIN_BLOCKS
 #define TR_TRAV_MIN_BLOCKS 8
 #endif
-template <int SLAB, bool COUNT>
+// WAIT: 0 = plain per-thread loop (traverse<>), > 0 = warp-synchronous loop with batched leaves (traverse_lb<>).
+// The grid-stride loop is warp-uniform (whole warps step together; lanes past the end of the queue are `valid ==
+// false`), which the warp-synchronous traversal needs and the plain one does not mind.
+template <int SLAB, bool COUNT, int WAIT>
 __global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_extend(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
                                                    const int* __restrict__ count, int cap, float4* __restrict__ hits,
                                                    unsigned long long* counters, int* error_flag) {
     const int n = min(*count, cap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o = ro[i], d = rd[i];
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        const bool valid = i < n;
+        const float4 o = valid ? ro[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = valid ? rd[i] : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         HitRecord h;
         // closest hit; the third barycentric is rebuilt exactly in the shade stage from the winning triangle
-        traverse<SLAB, false, COUNT>(sc, xyz(o), xyz(d), o.w, h, counters, error_flag);
-        hits[i] = make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1);
+        traverse_any<SLAB, false, COUNT, WAIT>(sc, valid, xyz(o), xyz(d), o.w, h, counters, error_flag);
+        if (valid) hits[i] = make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1);
     }
 }
 
-template <int SLAB, bool COUNT>
+template <int SLAB, bool COUNT, int WAIT>
 __global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_shadow(DeviceScene sc, const float4* __restrict__ so, const float4* __restrict__ sd,
                                                    const float4* __restrict__ contrib, const int* __restrict__ count, int cap,
                                                    float4* __restrict__ accum, unsigned long long* counters, int* error_flag) {
     const int n = min(*count, cap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o = so[i], d = sd[i];
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        const bool valid = i < n;
+        const float4 o = valid ? so[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = valid ? sd[i] : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         HitRecord h;
-        if (!traverse<SLAB, true, COUNT>(sc, xyz(o), xyz(d), o.w, h, counters, error_flag)) {
+        if (!traverse_any<SLAB, true, COUNT, WAIT>(sc, valid, xyz(o), xyz(d), o.w, h, counters, error_flag) && valid) {
             const float4 c = contrib[i];
             atomicAdd(&accum[__float_as_int(d.w)], make_float4(c.x, c.y, c.z, 0.0f));   // 128-bit vector atomic (sm_90+)
         }
@@ -43,7 +52,7 @@ __global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_shadow(DeviceSce
 
 // persistent-warp variants (dynamic ray fetch, traverse.cuh)
 template <int SLAB>
-__global__ void __launch_bounds__(128) k_wh_extend_p(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
+__global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_extend_p(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
                                                      const int* __restrict__ count, int cap, float4* __restrict__ hits,
                                                      int* work_counter, int* error_flag) {
     const int n = min(*count, cap);
@@ -52,7 +61,7 @@ __global__ void __launch_bounds__(128) k_wh_extend_p(DeviceScene sc, const float
     });
 }
 template <int SLAB>
-__global__ void __launch_bounds__(128) k_wh_shadow_p(DeviceScene sc, const float4* __restrict__ so, const float4* __restrict__ sd,
+__global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_shadow_p(DeviceScene sc, const float4* __restrict__ so, const float4* __restrict__ sd,
                                                      const float4* __restrict__ contrib, const int* __restrict__ count, int cap,
                                                      float4* __restrict__ accum, int* work_counter, int* error_flag) {
     const int n = min(*count, cap);
@@ -78,18 +87,18 @@ __device__ __forceinline__ float third_barycentric(const DeviceScene& sc, uint32
 template <class... Args>
 static void launch_extend_plain(trace_ctx* c, int grid, Args... args) {
     c->kev_begin(0);
-    if (c->slab == 0) { if (c->count_nodes) k_wh_extend<0, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_extend<0, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
-    else if (c->slab == 2) { if (c->count_nodes) k_wh_extend<2, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_extend<2, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
-    else              { if (c->count_nodes) k_wh_extend<1, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_extend<1, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
+    trav_dispatch(c, [&](auto S, auto C_, auto W) {
+        k_wh_extend<decltype(S)::value, decltype(C_)::value, decltype(W)::value><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...);
+    });
     c->stats.kernel_launches++;
     c->kev_end();
 }
 template <class... Args>
 static void launch_shadow_plain(trace_ctx* c, int grid, Args... args) {
     c->kev_begin(1);
-    if (c->slab == 0) { if (c->count_nodes) k_wh_shadow<0, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_shadow<0, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
-    else if (c->slab == 2) { if (c->count_nodes) k_wh_shadow<2, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_shadow<2, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
-    else              { if (c->count_nodes) k_wh_shadow<1, true><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); else k_wh_shadow<1, false><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...); }
+    trav_dispatch(c, [&](auto S, auto C_, auto W) {
+        k_wh_shadow<decltype(S)::value, decltype(C_)::value, decltype(W)::value><<<persistent_grid(c, 16), 128, 0, c->cur_stream>>>(args...);
+    });
     c->stats.kernel_launches++;
     c->kev_end();
 }
@@ -103,7 +112,8 @@ static int* next_work_counter(trace_ctx* c) {
 }
 static void launch_extend(trace_ctx* c, int grid, DeviceScene sc, const float4* ro, const float4* rd, const int* count, int cap,
                           float4* hits, unsigned long long* counters, int* err) {
-    if (c->persist && !c->count_nodes && c->slab != 1) {
+    // dynamic ray fetch (pair walk): "persist" 1 = bounce levels >= 2 only (incoherent rays, long tails), 2 = every level
+    if ((c->persist == 2 || (c->persist == 1 && c->cur_level >= 2)) && !c->count_nodes && c->slab != 1) {
         c->kev_begin(0);
         int* wc = next_work_counter(c);
         if (c->slab == 0) k_wh_extend_p<0><<<occupancy_grid(c, k_wh_extend_p<0>, 128), 128, 0, c->cur_stream>>>(sc, ro, rd, count, cap, hits, wc, err);

@@ -26,8 +26,11 @@ struct WhittedLaunch {
     const WhittedFrame* frame;
     DeviceFilm film;
     int spp, max_depth;
-    long long slot_begin;      // first slot of this batch (global over the rank's tile list)
+    long long slot_begin;      // first slot of this batch (global over the rank's tile list); a multiple of 256 * spp
     int n_slots;
+    int tile_begin;            // slot_begin / (256 * spp): first entry of `tiles` this batch covers
+    int spp_shift;             // log2(spp) when spp is a power of two, else -1
+    int fused;                 // 1: no primary-ray queue - k_wh_primary generates and traces, shade / splat re-derive the ray
     const int* tiles;          // tile indices owned by this rank
     float4 *ro[2], *rd[2], *rw[2];   // ray queues: {o, tmax} {d, slot} {weight, -}
     float4* hits;              // {b2, prim+1 (bits), b0, b1}
@@ -39,34 +42,61 @@ struct WhittedLaunch {
     float4* film_rgbw;         // per film pixel: sum(L*w) rgb, sum(w)
 };
 
-__device__ __forceinline__ void slot_to_pixel(const WhittedLaunch& L, long long slot, int& px, int& py, int& s, int& tile) {
-    const int per_tile = 256 * L.spp;
-    const long long lt = slot / per_tile;
-    const int within = (int)(slot - lt * per_tile);
-    const int pix = within / L.spp;
-    s = within - pix * L.spp;
-    tile = L.tiles[lt];
-    const int tx = tile % L.film.tiles_x, ty = tile / L.film.tiles_x;
-    px = L.film.sb_x0 + tx * 16 + (pix & 15);
-    py = L.film.sb_y0 + ty * 16 + (pix >> 4);
+// slot (batch-local, 32-bit) -> pixel, sample, tile.  Batches start on tile boundaries, so no 64-bit arithmetic; with a
+// power-of-two spp (every config) the two divisions are shifts.
+__device__ __forceinline__ void slot_to_pixel(const WhittedLaunch& L, int i, int& px, int& py, int& s, int& tile) {
+    unsigned lt, pix;
+    const unsigned u = (unsigned)i;
+    if (L.spp_shift >= 0) {
+        lt = u >> (8 + L.spp_shift);
+        const unsigned within = u & ((256u << L.spp_shift) - 1u);
+        pix = within >> L.spp_shift;
+        s = (int)(within & ((1u << L.spp_shift) - 1u));
+    } else {
+        const unsigned per_tile = 256u * (unsigned)L.spp;
+        lt = u / per_tile;
+        const unsigned within = u - lt * per_tile;
+        pix = within / (unsigned)L.spp;
+        s = (int)(within - pix * (unsigned)L.spp);
+    }
+    tile = __ldg(&L.tiles[L.tile_begin + (int)lt]);
+    const int ty = tile / L.film.tiles_x, tx = tile - ty * L.film.tiles_x;
+    px = L.film.sb_x0 + tx * 16 + (int)(pix & 15u);
+    py = L.film.sb_y0 + ty * 16 + (int)(pix >> 4);
 }
 
+// the camera sample of a slot: film position (px + u0, py + u1) and its ray.  Pure function of (seed, pixel, sample),
+// so the fused path re-derives it in shade and splat instead of storing it.  Returns false for slots outside the
+// sample bounds (tiles overhang the image).
+__device__ __forceinline__ bool slot_film_position(const WhittedLaunch& L, uint64_t seed, int i, int& px, int& py, int& s, int& tile,
+                                                   uint32_t& pix, float& fx, float& fy) {
+    slot_to_pixel(L, i, px, py, s, tile);
+    if (px > L.film.sb_x1 || py > L.film.sb_y1) return false;
+    pix = (uint32_t)((py - L.film.sb_y0) * (L.film.sb_x1 - L.film.sb_x0 + 1) + (px - L.film.sb_x0));
+    fx = (float)px + rng_uniform(seed, pix, (uint32_t)s, 0);
+    fy = (float)py + rng_uniform(seed, pix, (uint32_t)s, 1);
+    return true;
+}
+__device__ __forceinline__ void slot_camera_ray(const DeviceCamera& cam, uint64_t seed, uint32_t pix, int s, float fx, float fy,
+                                                float3& o, float3& d) {
+    float l0 = 0.0f, l1 = 0.0f;
+    if (cam.lens_radius > 0.0f) { l0 = rng_uniform(seed, pix, (uint32_t)s, 2); l1 = rng_uniform(seed, pix, (uint32_t)s, 3); }
+    generate_camera_ray(cam, fx, fy, l0, l1, o, d);
+}
+
+// unfused path (instrumented passes): one camera ray per slot into the level-1 queue
 __global__ void __launch_bounds__(256) k_wh_generate(WhittedLaunch L) {
     const DeviceCamera cam = L.frame->cam;
     const uint64_t seed = L.frame->seed;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.n_slots; i += gridDim.x * blockDim.x) {
         int px, py, s, tile;
-        slot_to_pixel(L, L.slot_begin + i, px, py, s, tile);
+        uint32_t pix;
+        float fx, fy;
         L.accum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (px > L.film.sb_x1 || py > L.film.sb_y1) { L.filmpos[i] = make_float2(-1e30f, -1e30f); continue; }
-        const uint32_t pix = (uint32_t)((py - L.film.sb_y0) * (L.film.sb_x1 - L.film.sb_x0 + 1) + (px - L.film.sb_x0));
-        const float u0 = rng_uniform(seed, pix, (uint32_t)s, 0), u1 = rng_uniform(seed, pix, (uint32_t)s, 1);
-        const float fx = (float)px + u0, fy = (float)py + u1;
-        float l0 = 0.0f, l1 = 0.0f;
-        if (cam.lens_radius > 0.0f) { l0 = rng_uniform(seed, pix, (uint32_t)s, 2); l1 = rng_uniform(seed, pix, (uint32_t)s, 3); }
-        float3 o, d;
-        generate_camera_ray(cam, fx, fy, l0, l1, o, d);
+        if (!slot_film_position(L, seed, i, px, py, s, tile, pix, fx, fy)) { L.filmpos[i] = make_float2(-1e30f, -1e30f); continue; }
         L.filmpos[i] = make_float2(fx, fy);
+        float3 o, d;
+        slot_camera_ray(cam, seed, pix, s, fx, fy, o, d);
         const int q = queue_claim(&L.counters[1]);
         L.ro[0][q] = f4(o, TR_INF);
         L.rd[0][q] = f4(d, __int_as_float(i));
@@ -74,15 +104,52 @@ __global__ void __launch_bounds__(256) k_wh_generate(WhittedLaunch L) {
     }
 }
 
+// fused path: generate the camera ray of slot i and trace it right away - hit record i belongs to slot i, there is no
+// primary-ray queue (saves writing and re-reading 48 bytes per sample and one launch per batch)
+template <int SLAB, int WAIT>
+__global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_primary(WhittedLaunch L, int* error_flag) {
+    const DeviceCamera cam = L.frame->cam;
+    const uint64_t seed = L.frame->seed;
+    const int lane = threadIdx.x & 31;
+    int n_active = 0;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < L.n_slots; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        int px, py, s, tile;
+        uint32_t pix = 0;
+        float fx, fy;
+        const bool valid = i < L.n_slots && slot_film_position(L, seed, i, px, py, s, tile, pix, fx, fy);
+        float3 o = f3s(0.0f), d = f3s(1.0f);
+        if (valid) slot_camera_ray(cam, seed, pix, s, fx, fy, o, d);
+        HitRecord h;
+        traverse_any<SLAB, false, false, WAIT>(L.sc, valid, o, d, TR_INF, h, nullptr, error_flag);
+        if (i < L.n_slots) {
+            L.accum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            L.hits[i] = make_float4(h.t, __uint_as_float(valid ? h.prim : 0u), h.b0, h.b1);
+        }
+        n_active += __popc(__ballot_sync(0xffffffffu, valid));
+    }
+    if (lane == 0 && n_active) atomicAdd(&L.counters[1], n_active);     // rays traced at level 1 (statistics only)
+}
+
 __global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
     const int cur = (level - 1) & 1, nxt = level & 1;
-    const int n = min(L.counters[level], L.cap_rays);
+    const bool rederive = L.fused && level == 1;
+    const int n = rederive ? L.n_slots : min(L.counters[level], L.cap_rays);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 h = L.hits[i];
         const uint32_t prim1 = __float_as_uint(h.y);
         if (prim1 == 0u) continue;                          // miss: le(light, ray) == 0 (lights/light.jl:41)
-        const float4 o4 = L.ro[cur][i], d4 = L.rd[cur][i];
-        const float3 w = xyz(L.rw[cur][i]);
+        float4 o4, d4;
+        float3 w;
+        if (rederive) {
+            int px, py, s, tile;
+            uint32_t pix;
+            float fx, fy;
+            slot_film_position(L, L.frame->seed, i, px, py, s, tile, pix, fx, fy);
+            float3 o, dd;
+            slot_camera_ray(L.frame->cam, L.frame->seed, pix, s, fx, fy, o, dd);
+            o4 = f4(o, TR_INF); d4 = f4(dd, __int_as_float(i)); w = f3s(1.0f);
+        } else { o4 = L.ro[cur][i]; d4 = L.rd[cur][i]; w = xyz(L.rw[cur][i]); }
         float3 d = xyz(d4);
         if (d.x == 0.0f) d.x = 0.0f;                        // the ray as intersect! left it (check_direction!)
         if (d.y == 0.0f) d.y = 0.0f;
@@ -131,33 +198,98 @@ __global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
 
 // add_sample! with the reference's footprint / table indexing quirks (film.jl:134-164, Q4) and the clipping to the
 // FilmTile bounds of the sample's 16x16 tile (film.jl:120-125).
+struct SplatClip { float x0, y0, x1, y1; };      // pixels a sample of this tile may touch (tile bounds ^ crop window)
+__device__ __forceinline__ SplatClip splat_clip(const DeviceFilm& F, int tile) {
+    const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
+    const int bx0 = F.sb_x0 + tx * 16, by0 = F.sb_y0 + ty * 16;
+    const int bx1 = min(bx0 + 15, F.sb_x1), by1 = min(by0 + 15, F.sb_y1);
+    SplatClip c;
+    c.x0 = fmaxf(fmaxf(ceilf((float)bx0 - 0.5f - F.rx), (float)F.crop_x0), 1.0f);
+    c.y0 = fmaxf(fmaxf(ceilf((float)by0 - 0.5f - F.ry), (float)F.crop_y0), 1.0f);
+    c.x1 = fminf(floorf((float)bx1 - 0.5f + F.rx) + 1.0f, (float)F.crop_x1);
+    c.y1 = fminf(floorf((float)by1 - 0.5f + F.ry) + 1.0f, (float)F.crop_y1);
+    return c;
+}
+// does sample (dx, dy) touch pixel (x, y), and with which filter weight
+__device__ __forceinline__ bool splat_weight(const DeviceFilm& F, const SplatClip& c, float dx, float dy, float x, float y, float& wgt) {
+    const float p0x = fmaxf(ceilf(dx - F.rx), c.x0), p0y = fmaxf(ceilf(dy - F.ry), c.y0);
+    const float p1x = fminf(floorf(dx + F.rx) + 1.0f, c.x1), p1y = fminf(floorf(dy + F.ry) + 1.0f, c.y1);
+    if (x < p0x || x > p1x || y < p0y || y > p1y) return false;
+    const int oy = (int)clampf(floorf(fabsf((y - dy) * F.inv_ry * 16.0f)), 1.0f, 16.0f);
+    const int ox = (int)clampf(ceilf(fabsf((x - dx) * F.inv_rx * 16.0f)), 1.0f, 16.0f);
+    wgt = __ldg(&F.table[(oy - 1) * 16 + (ox - 1)]);
+    return true;
+}
+
+// One film atomic per (pixel, touched film pixel) instead of one per (sample, touched film pixel): with spp a multiple
+// of 16 the 16 lanes of a half-warp hold 16 samples of ONE pixel; their footprints lie in a small common window
+// ((2r + 3)^2 film pixels: 4 x 4 for the radius-1 filter of every config), so each lane takes one film pixel of the
+// window, gathers the 16 samples by shuffle and issues one 128-bit atomic (round 1: 9 atomics per sample, the kernel
+// was bound by L2 atomic throughput).  Other spp values use the per-sample path.
 __global__ void __launch_bounds__(256) k_wh_splat(WhittedLaunch L) {
     if (L.counters[IC_OVERFLOW]) return;                      // the host re-runs the batch in smaller pieces
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.n_slots; i += gridDim.x * blockDim.x) {
-        const float2 fp = L.filmpos[i];
-        if (fp.x < -1e29f) continue;
-        float4 a = L.accum[i];
-        if (isnan(a.x) || isnan(a.y) || isnan(a.z)) { a.x = 0.0f; a.y = 0.0f; a.z = 0.0f; }
-        int px, py, s, tile;
-        slot_to_pixel(L, L.slot_begin + i, px, py, s, tile);
-        const DeviceFilm& F = L.film;
-        const int tx = tile % F.tiles_x, ty = tile / F.tiles_x;
-        const int bx0 = F.sb_x0 + tx * 16, by0 = F.sb_y0 + ty * 16;
-        const int bx1 = min(bx0 + 15, F.sb_x1), by1 = min(by0 + 15, F.sb_y1);
-        const float tbx0 = fmaxf(ceilf((float)bx0 - 0.5f - F.rx), (float)F.crop_x0);
-        const float tby0 = fmaxf(ceilf((float)by0 - 0.5f - F.ry), (float)F.crop_y0);
-        const float tbx1 = fminf(floorf((float)bx1 - 0.5f + F.rx) + 1.0f, (float)F.crop_x1);
-        const float tby1 = fminf(floorf((float)by1 - 0.5f + F.ry) + 1.0f, (float)F.crop_y1);
-        const float dx = fp.x - 0.5f, dy = fp.y - 0.5f;
-        const float p0x = fmaxf(ceilf(dx - F.rx), fmaxf(tbx0, 1.0f)), p0y = fmaxf(ceilf(dy - F.ry), fmaxf(tby0, 1.0f));
-        const float p1x = fminf(floorf(dx + F.rx) + 1.0f, tbx1), p1y = fminf(floorf(dy + F.ry) + 1.0f, tby1);
-        for (float y = p0y; y <= p1y; y += 1.0f) {
-            const int oy = (int)clampf(floorf(fabsf((y - dy) * F.inv_ry * 16.0f)), 1.0f, 16.0f);
-            for (float x = p0x; x <= p1x; x += 1.0f) {
-                const int ox = (int)clampf(ceilf(fabsf((x - dx) * F.inv_rx * 16.0f)), 1.0f, 16.0f);
-                const float wgt = __ldg(&F.table[(oy - 1) * 16 + (ox - 1)]);
+    const DeviceFilm& F = L.film;
+    const uint64_t seed = L.frame->seed;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool grouped = (L.spp & 15) == 0;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < L.n_slots; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        int px = 0, py = 0, s, tile = 0;
+        uint32_t pix;
+        float fx = 0.0f, fy = 0.0f;
+        bool valid = i < L.n_slots;
+        if (valid) {
+            if (L.fused) valid = slot_film_position(L, seed, i, px, py, s, tile, pix, fx, fy);
+            else {
+                const float2 fp = L.filmpos[i];
+                valid = !(fp.x < -1e29f);
+                fx = fp.x; fy = fp.y;
+                slot_to_pixel(L, i, px, py, s, tile);
+            }
+        }
+        float4 a = valid ? L.accum[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (isnan(a.x) || isnan(a.y) || isnan(a.z)) { a.x = 0.0f; a.y = 0.0f; a.z = 0.0f; }      // sampler.jl:46
+        const float dx = fx - 0.5f, dy = fy - 0.5f;
+        if (!grouped) {
+            if (!valid) continue;
+            const SplatClip c = splat_clip(F, tile);
+            const float p0x = fmaxf(ceilf(dx - F.rx), c.x0), p0y = fmaxf(ceilf(dy - F.ry), c.y0);
+            const float p1x = fminf(floorf(dx + F.rx) + 1.0f, c.x1), p1y = fminf(floorf(dy + F.ry) + 1.0f, c.y1);
+            for (float y = p0y; y <= p1y; y += 1.0f)
+                for (float x = p0x; x <= p1x; x += 1.0f) {
+                    float wgt = 0.0f;
+                    splat_weight(F, c, dx, dy, x, y, wgt);
+                    const int ix = (int)x - F.crop_x0, iy = (int)y - F.crop_y0;
+                    atomicAdd(&L.film_rgbw[(size_t)iy * F.width + ix], make_float4(a.x * wgt, a.y * wgt, a.z * wgt, wgt));
+                }
+            continue;
+        }
+        // grouped: the half-warp's pixel (identical in its 16 lanes) and the window its samples can touch
+        const int g = lane & 15, gbase = lane & 16;
+        const SplatClip c = splat_clip(F, tile);
+        const float wx0 = ceilf((float)px - 0.5f - F.rx), wy0 = ceilf((float)py - 0.5f - F.ry);
+        const int wnx = (int)(floorf((float)px + 0.5f + F.rx) + 1.0f - wx0) + 1, wny = (int)(floorf((float)py + 0.5f + F.ry) + 1.0f - wy0) + 1;
+        const int n_targets = __shfl_sync(full, valid ? wnx * wny : 0, gbase);
+        const int n_loop = max(__shfl_sync(full, n_targets, 0), __shfl_sync(full, n_targets, 16));     // warp-uniform trip count
+        for (int j0 = 0; j0 < n_loop; j0 += 16) {
+            const int j = j0 + g;
+            const float x = wx0 + (float)(j % wnx), y = wy0 + (float)(j / wnx);
+            float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            bool any = false;
+            #pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const int src = gbase + k;
+                const float kx = __shfl_sync(full, dx, src), ky = __shfl_sync(full, dy, src);
+                const float ar = __shfl_sync(full, a.x, src), ag = __shfl_sync(full, a.y, src), ab = __shfl_sync(full, a.z, src);
+                float wgt;
+                if (j < n_targets && splat_weight(F, c, kx, ky, x, y, wgt)) {
+                    acc.x += ar * wgt; acc.y += ag * wgt; acc.z += ab * wgt; acc.w += wgt; any = true;
+                }
+            }
+            if (any) {
                 const int ix = (int)x - F.crop_x0, iy = (int)y - F.crop_y0;
-                atomicAdd(&L.film_rgbw[(size_t)iy * F.width + ix], make_float4(a.x * wgt, a.y * wgt, a.z * wgt, wgt));
+                atomicAdd(&L.film_rgbw[(size_t)iy * F.width + ix], acc);
             }
         }
     }
@@ -204,27 +336,40 @@ __global__ void k_wh_batch_stats(int* counters, unsigned long long* stats, int m
 // sync cost ~0.9 ms of GPU idle time per batch on B200: 17 launches to enqueue behind an empty stream).
 static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long count, int depth_guard, int* batch_flag = nullptr) {
     if (count <= 0) return 0;
+    const long long per_tile = 256ll * L.spp;
     L.slot_begin = begin;
     L.n_slots = (int)count;
+    L.tile_begin = (int)(begin / per_tile);                    // batches start on tile boundaries
+    // fused primary stage unless an instrumented pass needs the plain kernels (node counting)
+    L.fused = (c->fuse_primary && !c->count_nodes && c->slab != 1 && !(c->persist == 2)) ? 1 : 0;
     int* ic = ctx_icounters(c);
     unsigned long long* st = ctx_stats64(c);
     TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->cur_stream));
     TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), c->cur_stream)); c->work_slot = 0;
     TR_CUDA(c, cudaMemsetAsync(ic + IC_OVERFLOW, 0, sizeof(int), c->cur_stream));
     const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
-    k_wh_generate<<<g_stream, 256, 0, c->cur_stream>>>(L);
+    int* d_err = ctx_icounters_lane(c, 0) + IC_ERROR;
+    if (L.fused) {
+        c->kev_begin(0);
+        trav_dispatch(c, [&](auto S, auto C_, auto W) {
+            k_wh_primary<decltype(S)::value, decltype(W)::value><<<g_trav, 128, 0, c->cur_stream>>>(L, d_err);
+        });
+        c->kev_end();
+    } else k_wh_generate<<<g_stream, 256, 0, c->cur_stream>>>(L);
     c->stats.kernel_launches++;
     for (int level = 1; level <= L.max_depth; ++level) {
         const int cur = (level - 1) & 1;
-        launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap_rays,
-                      L.hits, st + ST_NODES, ctx_icounters_lane(c, 0) + IC_ERROR);
+        c->cur_level = level;
+        if (!(L.fused && level == 1))
+            launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap_rays,
+                          L.hits, st + ST_NODES, d_err);
         k_wh_shade<<<occupancy_grid(c, k_wh_shade, 128), 128, 0, c->cur_stream>>>(L, level);
         c->stats.kernel_launches++;
     }
     // one any-hit launch over the shadow rays of ALL bounce levels of the batch (they only feed the accumulators): a
     // single wide launch instead of max_depth launches that each wait for their slowest ray
     launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
-                  (const int*)(ic + 32), L.cap_shadow, L.accum, st + ST_NODES, ctx_icounters_lane(c, 0) + IC_ERROR);
+                  (const int*)(ic + 32), L.cap_shadow, L.accum, st + ST_NODES, d_err);
     k_wh_splat<<<g_stream, 256, 0, c->cur_stream>>>(L);
     k_wh_batch_stats<<<1, 32, 0, c->cur_stream>>>(ic, st, L.max_depth, L.cap_rays, L.cap_shadow, batch_flag);
     c->stats.kernel_launches += 2;
@@ -240,18 +385,29 @@ static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long 
     }
     if (c->h_flags[0]) {                                  // a queue overflowed: nothing was splatted, redo in halves
         c->stats.queue_overflows++;
-        if (count < 2048 || depth_guard > 24) return c->fail("ray queue overflow that halving the batch cannot resolve");
-        const long long half = count / 2;
+        if (count < 2 * per_tile || depth_guard > 24) return c->fail("ray queue overflow that halving the batch cannot resolve");
+        const long long half = count / 2 / per_tile * per_tile;
         if (run_batch(c, L, begin, half, depth_guard + 1)) return 1;
         return run_batch(c, L, begin + half, count - half, depth_guard + 1);
     }
     return 0;
 }
 
+// Film pixels [*p0, *p1) (row-major) this rank's film receives: everything on one GPU; with a communicator either the whole
+// film on rank 0 and nothing elsewhere (film_mode 0) or the rank's chunk of ceil(n / world) pixels (film_mode 1).
+void whitted_film_range(const trace_ctx* c, long long npix, long long* p0, long long* p1) {
+    *p0 = 0; *p1 = npix;
+    if (!c->comm || c->world <= 1) return;
+    if (c->film_mode == 0) { if (c->rank != 0) *p1 = 0; return; }
+    const long long chunk = (npix + c->world - 1) / c->world;
+    *p0 = std::min(npix, (long long)c->rank * chunk);
+    *p1 = std::min(npix, *p0 + chunk);
+}
+
 int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_film_desc* film, int spp, int max_depth,
                           uint64_t seed, float* film_dev) {
     if (c->rank < 0 || c->rank >= c->world) return c->fail("rank %d outside world %d", c->rank, c->world);
-    if (max_depth > 28) return c->fail("max_depth too large");
+    if (max_depth < 1 || max_depth > TR_MAX_DEPTH) return c->fail("max_depth must be in [1, %d]", TR_MAX_DEPTH);
     WhittedLaunch L;
     memset(&L, 0, sizeof(L));                                   // padding too: the struct's bytes key the graph cache
     L.sc = c->scene;
@@ -264,6 +420,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     L.frame = c->b_misc[3].as<WhittedFrame>();
     if (ctx_device_film(c, film, &L.film, &c->b_misc[0])) return 1;
     L.spp = spp; L.max_depth = max_depth;
+    L.spp_shift = (spp & (spp - 1)) == 0 ? __builtin_ctz((unsigned)spp) : -1;
     // this rank's tiles: k = rank, rank + world, ...   (16x16 sample tiles, sampler.jl:24-31)
     const int total_tiles = L.film.tiles_x * L.film.tiles_y;
     std::vector<int> tiles;
@@ -278,8 +435,10 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     const long long per_lane = std::max<long long>(65536, c->batch / K);
     long long nb = std::max<long long>(K, (total_slots + per_lane - 1) / per_lane);
     nb = (nb + K - 1) / K * K;                                  // whole rounds of K lanes
+    const long long per_tile = 256ll * spp;
     long long batch = (total_slots + nb - 1) / nb;
-    batch = std::max<long long>(256, (batch + 255) / 256 * 256);
+    batch = std::max<long long>(per_tile, (batch + per_tile - 1) / per_tile * per_tile);     // whole tiles: 32-bit slot math in the kernels
+    if (batch > 0x7fffffffll / 2) return c->fail("batch too large: set option \"batch\" below 2^30 samples");
     nb = (total_slots + batch - 1) / batch;
     {
         // Batches are contiguous slot ranges, i.e. runs of the tile list.  In image order a run is a band of the image,
@@ -317,7 +476,8 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     TR_CUDA(c, c->b_queue[10].ensure((size_t)K * batch * sizeof(float4)));
     TR_CUDA(c, c->b_queue[11].ensure((size_t)K * batch * sizeof(float2)));
     const size_t npix = (size_t)L.film.width * L.film.height;
-    TR_CUDA(c, c->b_queue[12].ensure(npix * sizeof(float4)));
+    const size_t npix_padded = (npix + (size_t)c->world - 1) / (size_t)c->world * (size_t)c->world;     // equal chunks for the reduce-scatter
+    TR_CUDA(c, c->b_queue[12].ensure(npix_padded * sizeof(float4)));
     L.film_rgbw = c->b_queue[12].as<float4>();
     std::vector<WhittedLaunch> lane((size_t)K, L);
     for (int l = 0; l < K; ++l) {
@@ -336,7 +496,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     // everything up to the lanes' join: film clear, then batch bi on lane bi % K
     auto enqueue = [&]() -> int {
-        TR_CUDA(c, cudaMemsetAsync(L.film_rgbw, 0, npix * sizeof(float4), c->stream));
+        TR_CUDA(c, cudaMemsetAsync(L.film_rgbw, 0, npix_padded * sizeof(float4), c->stream));
         if (K > 1) {
             TR_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
             for (int l = 0; l < K; ++l) TR_CUDA(c, cudaStreamWaitEvent(c->side[l], c->ev_fork, 0));
@@ -362,7 +522,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     if (c->graph && !c->time_kernels && (size_t)c->stream > 2) {       // (legacy / per-thread default streams cannot be captured)
         std::string key((const char*)lane.data(), lane.size() * sizeof(WhittedLaunch));
         key.append((const char*)b_count.data(), b_count.size() * sizeof(long long));
-        const long long extra[] = {nb, batch, K, total_slots, (long long)(size_t)d_flags, c->slab, c->persist, c->count_nodes,
+        const long long extra[] = {nb, batch, K, total_slots, (long long)(size_t)d_flags, c->slab, c->persist, c->count_nodes, c->leaf_wait, c->fuse_primary,
                                    (long long)(size_t)c->stream};
         key.append((const char*)extra, sizeof(extra));
         if (!c->wh_graph || key != c->wh_graph_key) {
@@ -390,13 +550,20 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
         rc = enqueue();
     }
     if (rc) return 1;
-    // optimistic tail: fold the flags, merge the film unless something went wrong, read the flags back - ONE host wait
     int* d_err = ctx_icounters_lane(c, 0) + IC_ERROR;
+    const bool multi = c->comm != nullptr && c->world > 1;
+    long long f0 = 0, f1 = (long long)npix;                     // film pixels this rank delivers
+    whitted_film_range(c, (long long)npix, &f0, &f1);
+    // fold the flags, [single rank: merge the film unless something went wrong,] read the flags back
     k_wh_any_flag<<<1, 32, 0, c->stream>>>(d_flags, (int)nb, d_err, d_flags + nb);
-    if (c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
-    k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix, d_flags + nb);
-    c->stats.kernel_launches += 2;
-    TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->stats.kernel_launches++;
+    if (!multi) {
+        // optimistic: the merge is already enqueued behind the render - ONE host wait per render
+        if (c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
+        k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix, d_flags + nb);
+        c->stats.kernel_launches++;
+        TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    }
     std::vector<int> h_flags((size_t)nb + 2, 0);
     TR_CUDA(c, cudaMemcpyAsync(h_flags.data(), d_flags, (size_t)(nb + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     TR_CUDA(c, cudaMemcpyAsync(&h_flags[(size_t)nb + 1], d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -404,18 +571,38 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     c->kev_collect();
     if (h_flags[(size_t)nb + 1]) {
         cudaMemsetAsync(d_err, 0, sizeof(int), c->stream);
+        // (multi-rank: the other ranks are left waiting in the film sum - a traversal error is fatal for the job)
         return c->fail("traversal stack overflow (more than 64 pending nodes; the reference would throw a BoundsError, bvh.jl:222)");
     }
     if (h_flags[(size_t)nb]) {
         for (long long bi = 0; bi < nb; ++bi) {
             if (!h_flags[bi]) continue;                     // overflowed batches were not splatted: redo them in halves
             c->stats.queue_overflows++;
-            const long long b = b_begin[bi], cnt = b_count[bi], half = cnt / 2;
-            if (cnt < 2048) return c->fail("ray queue overflow that halving the batch cannot resolve");
+            const long long b = b_begin[bi], cnt = b_count[bi], half = cnt / 2 / per_tile * per_tile;
+            if (cnt < 2 * per_tile) return c->fail("ray queue overflow that halving the batch cannot resolve");
             if (run_batch(c, lane[0], b, half, 1) || run_batch(c, lane[0], b + half, cnt - half, 1)) return 1;
         }
-        k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix, nullptr);
-        c->stats.kernel_launches++;
+        if (!multi) {
+            k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix, nullptr);
+            c->stats.kernel_launches++;
+            TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+            TR_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+    }
+    if (multi) {
+        // the ONE exchange of a Whitted render: sum of the ranks' private films, on the render's stream
+        float* rgbw = reinterpret_cast<float*>(L.film_rgbw);
+        const float4* merged = L.film_rgbw;
+        if (c->film_mode == 0) { if (comm_reduce_sum(c, rgbw, rgbw, npix * 4, 0)) return 1; }
+        else {
+            const size_t chunk = (npix + (size_t)c->world - 1) / (size_t)c->world;
+            if (comm_reduce_scatter_sum(c, rgbw, rgbw + (size_t)c->rank * chunk * 4, chunk * 4)) return 1;     // in place
+        }
+        if (f1 > f0) {
+            if (c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
+            k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(merged + f0, (float4*)film_dev + f0, (int)(f1 - f0), nullptr);
+            c->stats.kernel_launches++;
+        }
         TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
         TR_CUDA(c, cudaStreamSynchronize(c->stream));
     }
