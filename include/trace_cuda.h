@@ -117,6 +117,10 @@ typedef struct trace_film_desc {
     float scale;
 } trace_film_desc;
 
+/* kernel classes of the per-class timing in trace_stats */
+enum { TRACE_K_EXTEND = 0, TRACE_K_SHADOW = 1, TRACE_K_GENERATE = 2, TRACE_K_SHADE = 3, TRACE_K_SPLAT = 4,
+       TRACE_K_GRID = 5 /* SPPM hash grid: bounds, count, scan, fill */, TRACE_K_DEPOSIT = 6, TRACE_K_UPDATE = 7,
+       TRACE_K_COUNT = 8 };
 typedef struct trace_stats {
     uint64_t rays_extend;        /* rays through closest-hit traversal */
     uint64_t rays_shadow;        /* rays through any-hit traversal */
@@ -130,6 +134,15 @@ typedef struct trace_stats {
     uint64_t sppm_deposits;
     uint64_t extend_launches;    /* closest-hit kernel launches timed into ms_extend */
     uint64_t shadow_launches;    /* any-hit kernel launches timed into ms_shadow */
+    /* option "time_kernels": CUDA-event time and launch count per kernel class (TRACE_K_*); [0] and [1] repeat
+     * ms_extend / ms_shadow */
+    double   ms_kind[TRACE_K_COUNT];
+    uint64_t launches_kind[TRACE_K_COUNT];
+    uint64_t sppm_candidates;    /* visible points examined by photon deposits (16 B each, streamed) */
+    uint64_t sppm_requests;      /* photon deposit requests (photon-surface hits at depth > 1) */
+    uint64_t sppm_grid_items;    /* (visible point, grid cell) entries inserted */
+    uint64_t primary_rays;       /* Whitted: camera rays traced ... */
+    uint64_t primary_hits;       /* ... and how many of them hit something (the rest leave the scene after a few box tests) */
 } trace_stats;
 
 typedef struct trace_ctx trace_ctx;
@@ -238,6 +251,10 @@ void* trace_sppm_buffer_device(trace_ctx* ctx, int which /* 0 flux, 1 Ld, 2..6 v
 int   trace_sppm_update(trace_ctx* ctx);
 int   trace_sppm_image(trace_ctx* ctx, int iteration, float* rgb_out);
 int   trace_sppm_end(trace_ctx* ctx);
+/* session form of trace_render_sppm's loop: after trace_sppm_begin, enqueue iterations first .. first + n - 1 back to
+ * back (no host wait; with a communicator the all-gather / all-reduce of every iteration run inside); read the image
+ * with trace_sppm_image (which waits and reports any queue / grid overflow), finish with trace_sppm_end. */
+int   trace_sppm_iterate(trace_ctx* ctx, int first_iteration, int n);
 
 #ifdef __cplusplus
 }

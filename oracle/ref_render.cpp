@@ -124,10 +124,12 @@ extern "C" int ref_render_whitted(const ref_scene* rs, const trace_camera* cam, 
                                   uint64_t* ray_counters) {
     return render_whitted_impl(rs, cam, film, spp, max_depth, seed, film_xyzw, n_threads, max_tiles, ray_counters, nullptr, -1);
 }
-// explicit tile list (k = ty * n_tiles_x + tx), single thread: used to check the multi-GPU tile partition on CPU
+// explicit tile list (k = ty * n_tiles_x + tx): used to check the multi-GPU tile partition on CPU and to compare full-size
+// films over one rank's share of the tiles
 extern "C" int ref_render_whitted_tiles(const ref_scene* rs, const trace_camera* cam, const trace_film_desc* film, int spp,
-                                        int max_depth, uint64_t seed, float* film_xyzw, const int64_t* tiles, int64_t n_tiles) {
-    return render_whitted_impl(rs, cam, film, spp, max_depth, seed, film_xyzw, 1, 0, nullptr, tiles, n_tiles);
+                                        int max_depth, uint64_t seed, float* film_xyzw, const int64_t* tiles, int64_t n_tiles,
+                                        int n_threads, uint64_t* ray_counters) {
+    return render_whitted_impl(rs, cam, film, spp, max_depth, seed, film_xyzw, n_threads < 1 ? 1 : n_threads, 0, ray_counters, tiles, n_tiles);
 }
 
 static int render_whitted_impl(const ref_scene* rs, const trace_camera* cam, const trace_film_desc* film, int spp,

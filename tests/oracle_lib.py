@@ -36,6 +36,7 @@ def lib():
         L.ref_hit_record.argtypes = [P, P, P, C.c_float, P]
         L.ref_prim_hit_record.argtypes = [P, C.c_int64, P, P, C.c_float, P]
         L.ref_render_whitted.argtypes = [P, P, P, C.c_int, C.c_int, C.c_uint64, P, C.c_int, C.c_int64, P]
+        L.ref_render_whitted_tiles.argtypes = [P, P, P, C.c_int, C.c_int, C.c_uint64, P, P, C.c_int64, C.c_int, P]
         L.ref_render_sppm.argtypes = [P, P, P, C.c_float, C.c_int, C.c_int, C.c_int64, C.c_uint64, P, C.c_int, P]
         L.ref_bounds_intersect.argtypes = [P, P, P, P, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.ref_bounds_intersect_p.argtypes = [P, P, P, P, C.c_float, C.c_int]
@@ -132,6 +133,15 @@ class OracleScene:
         cnt = np.zeros(2, np.uint64)
         rc = lib().ref_render_whitted(self.h, C.byref(cam), C.byref(fd), spp, max_depth, C.c_uint64(seed), p(film_xyzw),
                                       threads or self.threads, max_tiles, p(cnt))
+        assert rc == 0
+        return cnt
+
+    def render_whitted_tiles(self, cam, fd, spp, max_depth, seed, film_xyzw, tiles, threads=None):
+        """Only the 16x16 sample tiles in `tiles` (k = ty * n_tiles_x + tx), e.g. one rank's share k % world == rank."""
+        cnt = np.zeros(2, np.uint64)
+        tl = np.ascontiguousarray(tiles, dtype=np.int64)
+        rc = lib().ref_render_whitted_tiles(self.h, C.byref(cam), C.byref(fd), spp, max_depth, C.c_uint64(seed), p(film_xyzw),
+                                            p(tl), len(tl), threads or self.threads, p(cnt))
         assert rc == 0
         return cnt
 

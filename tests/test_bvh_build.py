@@ -147,3 +147,41 @@ def test_optin_sah_tree_same_hits_less_work(T):
     # where the later primitive in traversal order wins (Q13) and the order is the tree's
     assert (a[0] != b[0]).mean() < 1e-3
     assert float(b[3][0]) < 0.7 * float(a[3][0])                                 # fewer box tests (literal slab: 0.59x)
+
+
+def test_threaded_build_is_bit_identical(T, monkeypatch):
+    """The multi-threaded build (parallel passes over the large nodes + independent subtree jobs, then stitched into
+    preorder) must produce the one-threaded array bit for bit - and that one equals the oracle's (the reference's split
+    logic).  200 000 clustered boxes: above the 65 536-primitive job threshold, so the top phase, the jobs and the
+    stitching are all exercised; both builders."""
+    import ctypes as C
+    from trace_jl_b200 import _lib as tl
+    lib = tl.load()
+    rng = np.random.default_rng(3)
+    n = 200_000
+    c = rng.normal(size=(n, 3)).astype(np.float32) * np.array([40, 3, 15], np.float32) + rng.integers(0, 4, (n, 1)).astype(np.float32) * 30
+    e = rng.uniform(0.0, 0.4, (n, 3)).astype(np.float32)
+    e[rng.uniform(size=n) < 0.1] = 0                       # points: zero-extent boxes
+    bounds = np.ascontiguousarray(np.concatenate([c - e, c + e], 1), dtype=np.float32)
+
+    def build(fn, m):
+        h = C.c_void_p()
+        assert fn(tl.ptr(bounds), n, m, C.byref(h)) == 0
+        nodes = np.zeros(lib.trace_bvh_num_nodes(h), dtype=tl.node_dtype)
+        order = np.zeros(lib.trace_bvh_num_prims(h), dtype=np.uint32)
+        lib.trace_bvh_copy(h, tl.ptr(nodes), tl.ptr(order))
+        lib.trace_bvh_free(h)
+        return nodes, order
+
+    for fn, m in ((lib.trace_bvh_build, 1), (lib.trace_bvh_build, 4), (lib.trace_bvh_build_sah, 4)):
+        monkeypatch.setenv("TRACE_BVH_THREADS", "1")
+        n1, o1 = build(fn, m)
+        for threads in ("2", "7"):
+            monkeypatch.setenv("TRACE_BVH_THREADS", threads)
+            nt, ot = build(fn, m)
+            assert n1.tobytes() == nt.tobytes() and np.array_equal(o1, ot), (fn, m, threads)
+        assert sorted(o1.tolist()) == list(range(n))
+    monkeypatch.setenv("TRACE_BVH_THREADS", "5")
+    nt, ot = build(lib.trace_bvh_build, 1)
+    rn, ro, _ = oracle_lib.bvh_build(bounds, 1)
+    assert rn.tobytes() == nt.tobytes() and np.array_equal(ro, ot)

@@ -96,6 +96,7 @@ def check_scene(T, ctx, scene, camera, n, seed, label):
     for name, (o, d, tmax) in ray_sets(T, scene, camera, n, seed).items():
         rprim, rt, rb = osc.intersect(o, d, tmax, slab=0)
         rocc = osc.occluded(o, d, tmax, slab=0)
+        ctx.set_option("walk", 0)               # the reference loop (one node per step) first
         for slab in (0, 1, 2):
             ctx.set_option("slab", slab)
             prim, t, b = ctx.intersect(o, d, tmax)
@@ -140,8 +141,7 @@ def check_scene(T, ctx, scene, camera, n, seed, label):
             assert np.array_equal(t.view(np.uint32), rt.view(np.uint32)), f"{label}/{name}/slab{slab}/pair: t differs"
             assert np.array_equal(b.view(np.uint32), rb.view(np.uint32)), f"{label}/{name}/slab{slab}/pair: barycentrics differ"
             assert np.array_equal(occ, rocc), f"{label}/{name}/slab{slab}/pair: any-hit differs"
-        ctx.set_option("walk", 0)
-        ctx.set_option("slab", 2)
+        ctx.set_option("slab", 2)               # back to the defaults: guarded box test, pair-node walk
     for s in summary:
         print("parity", *s)
     return summary

@@ -143,9 +143,7 @@ mine = D.tile_shard(n_tiles, rank, world)
 film = np.zeros_like(camera.film.pixels)
 import ctypes as C
 L = oracle_lib.lib()
-L.ref_render_whitted_tiles.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64]
-tl = np.array(mine, np.int64)
-assert L.ref_render_whitted_tiles(osc.h, C.byref(cam), C.byref(fd), 2, 4, C.c_uint64(9), oracle_lib.p(film), oracle_lib.p(tl), len(tl)) == 0
+osc.render_whitted_tiles(cam, fd, 2, 4, 9, film, mine, threads=1)
 t = torch.from_numpy(film)
 D.allreduce_sum(t)
 full = np.zeros_like(film)
@@ -166,6 +164,9 @@ for y_ in range(H_):
         assert whole[D.raster_to_storage(x_, y_, W_, H_, world)].item() == float(y_ * W_ + x_)
 # SPPM photon slices partition the iteration
 b, e = D.photon_range(1000, rank, world)
+# the communicator id travels from rank 0 to everybody (distributed.init_comm); here with a stand-in id, on gloo
+cid = D.broadcast_id(lambda: bytes(range(128)), rank)
+assert cid == bytes(range(128)), rank
 cnt = torch.tensor([float(e - b)])
 D.allreduce_sum(cnt)
 assert cnt.item() == 1000

@@ -15,6 +15,6 @@ from .geometry import (Bounds2, Bounds3, Normal3f, Point2f, Point3f, Transformat
 from .scene import (BVHAccel, ConstantTexture, DirectionalLight, FlatScene, GeometricPrimitive, GlassMaterial, MatteMaterial, MirrorMaterial,
                     PlasticMaterial, PointLight, PrimitiveBatch, RGBSpectrum, Scene, ShapeCore, Sphere, SpotLight, Triangle,
                     TriangleMesh, TriangleSet, create_triangle_mesh, load_triangle_mesh)
-from .render import (Context, Film, LanczosSincFilter, PerspectiveCamera, SPPMIntegrator, UniformSampler, WhittedIntegrator,
+from .render import (Context, comm_unique_id, Film, LanczosSincFilter, PerspectiveCamera, SPPMIntegrator, UniformSampler, WhittedIntegrator,
                      default_context, write_png)
 from . import scenes  # noqa: E402

@@ -52,10 +52,17 @@ class Stats(C.Structure):
     _fields_ = [("rays_extend", C.c_uint64), ("rays_shadow", C.c_uint64), ("nodes_visited", C.c_uint64),
                 ("prims_tested", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_extend", C.c_double),
                 ("ms_shadow", C.c_double), ("ms_total", C.c_double), ("queue_overflows", C.c_uint64),
-                ("sppm_deposits", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64)]
+                ("sppm_deposits", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
+                ("ms_kind", C.c_double * 8), ("launches_kind", C.c_uint64 * 8), ("sppm_candidates", C.c_uint64),
+                ("sppm_requests", C.c_uint64), ("sppm_grid_items", C.c_uint64), ("primary_rays", C.c_uint64),
+                ("primary_hits", C.c_uint64)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k in ("ms_kind", "launches_kind") else getattr(self, k)) for k, _ in self._fields_}
+
+
+K_EXTEND, K_SHADOW, K_GENERATE, K_SHADE, K_SPLAT, K_GRID, K_DEPOSIT, K_UPDATE = range(8)
+KIND_NAMES = ["extend", "shadow", "generate", "shade", "splat", "grid", "deposit", "update"]
 
 
 SPPM_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float))
@@ -100,6 +107,7 @@ SIGNATURES = {
     "trace_sppm_update": (C.c_int, [_P]),
     "trace_sppm_image": (C.c_int, [_P, C.c_int, _P]),
     "trace_sppm_end": (C.c_int, [_P]),
+    "trace_sppm_iterate": (C.c_int, [_P, C.c_int, C.c_int]),
 }
 
 _lib = None

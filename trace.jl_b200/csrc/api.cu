@@ -109,7 +109,7 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     if (!strcmp(key, "slab")) { if (v < 0 || v > 2) return c->fail("slab must be 0 (literal), 1 (textbook) or 2 (guarded)"); c->slab = (int)v; }
     else if (!strcmp(key, "batch")) { if (v < 1024) return c->fail("batch too small"); c->batch = v; }
     else if (!strcmp(key, "count_nodes")) c->count_nodes = v != 0;
-    else if (!strcmp(key, "persist")) { if (v < 0 || v > 2) return c->fail("persist must be 0, 1 or 2"); c->persist = (int)v; }
+    else if (!strcmp(key, "persist")) { if (v != 0) return c->fail("persist: the dynamic-ray-fetch kernels were measured slower in both rounds and removed (profiles/r2_experiments.md)"); }
     else if (!strcmp(key, "film_mode")) { if (v != 0 && v != 1) return c->fail("film_mode must be 0 (whole film on rank 0) or 1 (one band per rank)"); c->film_mode = (int)v; }
     else if (!strcmp(key, "fuse_primary")) c->fuse_primary = v != 0;
     else if (!strcmp(key, "walk")) { if (v != 0 && v != 1) return c->fail("walk must be 0 (one node per step, the reference loop) or 1 (pair nodes)"); c->leaf_wait = v ? TR_WALK_PAIR : 0; }
@@ -136,6 +136,11 @@ int ctx_pull_stats(trace_ctx* c) {
     c->stats.nodes_visited = h[ST_NODES];
     c->stats.prims_tested = h[ST_PRIMS];
     c->stats.sppm_deposits = h[ST_DEPOSITS];
+    c->stats.sppm_candidates = h[ST_CANDIDATES];
+    c->stats.sppm_requests = h[ST_REQUESTS];
+    c->stats.sppm_grid_items = h[ST_GRID_ITEMS];
+    c->stats.primary_rays = h[ST_PRIMARY_RAYS];
+    c->stats.primary_hits = h[ST_PRIMARY_HITS];
     return 0;
 }
 
@@ -348,7 +353,7 @@ extern "C" int trace_scene_upload(trace_ctx* c, const trace_scene_desc* d) {
         }
     }
     c->have_scene = true;
-    sppm_free(c);
+    sppm_end_session(c);
     return 0;
 }
 
@@ -419,7 +424,8 @@ static int finish_query(trace_ctx* c, int stat_slot, int64_t n, bool is_shadow) 
     if (c->time_kernels) {
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, c->evk0, c->evk1);
-        if (is_shadow) { c->stats.ms_shadow += ms; c->stats.shadow_launches++; } else { c->stats.ms_extend += ms; c->stats.extend_launches++; }
+        if (is_shadow) { c->stats.ms_shadow += ms; c->stats.shadow_launches++; c->stats.ms_kind[TRACE_K_SHADOW] += ms; c->stats.launches_kind[TRACE_K_SHADOW]++; }
+        else { c->stats.ms_extend += ms; c->stats.extend_launches++; c->stats.ms_kind[TRACE_K_EXTEND] += ms; c->stats.launches_kind[TRACE_K_EXTEND]++; }
     }
     if (c->h_flags[1]) {
         cudaMemsetAsync(ctx_icounters(c) + IC_ERROR, 0, sizeof(int), c->stream);

@@ -7,16 +7,27 @@
 // [from..mid] | [mid+1..to], two-primitive nodes split at the smaller centroid, zero-primitive leaves kept.
 // Unlike the reference's recursive, allocation-per-node build this one is iterative: SoA bounds/centroids, one index
 // permutation that is partitioned in place, and nodes emitted directly in the flattened preorder (first child =
-// parent + 1), so building the 10 M-triangle scene needs no recursion and no per-node heap traffic.
+// parent + 1), so building the 10 M-triangle scene needs no recursion and no per-node heap traffic.  It is also
+// multi-threaded (std::thread; TRACE_BVH_THREADS overrides the thread count): the passes over large nodes run in
+// parallel and subtrees below 65 536 primitives are independent jobs - with the one-threaded result bit for bit.
 // Compiled with -ffp-contract=off: the cost arithmetic must round like the reference's.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <cstdlib>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/trace_cuda.h"
+
+struct trace_bvh {
+    std::vector<trace_bvh_node> nodes;
+    std::vector<uint32_t> order;
+};
 
 namespace {
 
@@ -60,176 +71,155 @@ struct Box {
     }
 };
 
-struct Task { int64_t from, to; int64_t patch; };   // inclusive range into the permutation; node whose `offset` we are
-
-}  // namespace
-
-struct trace_bvh {
-    std::vector<trace_bvh_node> nodes;
-    std::vector<uint32_t> order;
-};
-
-extern "C" int trace_bvh_build(const float* pb, int64_t n, int max_node_primitives, trace_bvh** out) {
-    if (!out || n < 0 || (n > 0 && !pb)) return 1;
-    *out = nullptr;
-    trace_bvh* bvh = new (std::nothrow) trace_bvh();
-    if (!bvh) return 2;
-    if (n == 0) { *out = bvh; return 0; }
-    const int max_prims = max_node_primitives < 255 ? max_node_primitives : 255;
-    const int NB = 12;
-    std::vector<float> cen((size_t)n * 3);
-    std::vector<uint32_t> perm((size_t)n);
-    for (int64_t i = 0; i < n; ++i) {
-        perm[i] = (uint32_t)i;
-        for (int k = 0; k < 3; ++k) cen[3 * i + k] = 0.5f * pb[6 * i + k] + 0.5f * pb[6 * i + 3 + k];
-    }
-    try {
-        bvh->nodes.reserve((size_t)(2 * n + 16));
-        bvh->order.reserve((size_t)n);
-    } catch (...) { delete bvh; return 2; }
-
-    std::vector<Task> todo;
-    todo.push_back({0, n - 1, -1});
-    const int64_t node_limit = 8 * n + 1024;     // a guard, never reached by terminating inputs
-    while (!todo.empty()) {
-        const Task t = todo.back();
-        todo.pop_back();
-        const int64_t slot = (int64_t)bvh->nodes.size();
-        if (slot > node_limit) { delete bvh; return 3; }
-        if (t.patch >= 0) bvh->nodes[t.patch].offset = (uint32_t)slot;
-        const int64_t count = t.to - t.from + 1;
-
-        Box all; all.reset();
-        for (int64_t i = t.from; i <= t.to; ++i) { const float* b = pb + 6 * (size_t)perm[i]; all.grow(b, b + 3); }
-        trace_bvh_node node;
-        for (int k = 0; k < 3; ++k) { node.bmin[k] = all.lo[k]; node.bmax[k] = all.hi[k]; }
-
-        bool leaf = (count == 1);
-        int axis = 0;
-        Box cb; cb.reset();
-        if (!leaf) {
-            for (int64_t i = t.from; i <= t.to; ++i) { const float* c = &cen[3 * (size_t)perm[i]]; cb.grow(c, c); }
-            axis = cb.widest();
-            if (!cb.valid() || cb.lo[axis] == cb.hi[axis]) leaf = true;
-        }
-        int64_t mid = t.from;
-        if (!leaf) {
-            // relative position of a centroid along `axis`, bounds.jl:134-143 (offset)
-            const bool any_extent = cb.hi[0] > cb.lo[0] || cb.hi[1] > cb.lo[1] || cb.hi[2] > cb.lo[2];
-            const float extent = cb.hi[axis] > cb.lo[axis] ? cb.hi[axis] - cb.lo[axis] : 1.0f;
-            auto bucket = [&](uint32_t prim) -> int {
-                float o = cen[3 * (size_t)prim + axis] - cb.lo[axis];
-                if (any_extent) o = o / extent;
-                int b = (int)std::floor(12.0f * o);
-                return b == NB ? NB - 1 : b;
-            };
-            if (count <= 2) {
-                // partialsort!(view, 1, by = centroid[axis]) on two entries; mid = (from + to) ÷ 2 = from
-                if (cen[3 * (size_t)perm[t.to] + axis] < cen[3 * (size_t)perm[t.from] + axis]) std::swap(perm[t.from], perm[t.to]);
-                mid = (t.from + t.to) / 2;
-            } else {
-                Box bk[NB];
-                for (int b = 0; b < NB; ++b) bk[b].point(0.0f);
-                for (int64_t i = t.from; i <= t.to; ++i) {
-                    const uint32_t p = perm[i];
-                    const float* b = pb + 6 * (size_t)p;
-                    bk[bucket(p)].grow(b, b + 3);
-                }
-                // prefix unions 0..i and suffix unions i..10 (bucket 11 never enters the right-hand side)
-                Box pre[NB], suf[NB];
-                pre[0] = bk[0];
-                for (int b = 1; b < NB; ++b) { pre[b] = pre[b - 1]; pre[b].grow(bk[b]); }
-                // the reference folds the right side left-to-right starting at bucket i+1; min/max are exact, so a
-                // suffix scan yields the same box
-                suf[NB - 2] = bk[NB - 2];
-                for (int b = NB - 3; b >= 0; --b) { suf[b] = bk[b]; suf[b].grow(suf[b + 1]); }
-                const float total_area = all.area();
-                int best = 0;
-                float best_cost = 0.0f;
-                bool best_nan = false;
-                for (int i = 0; i < NB - 1; ++i) {            // split after bucket i (0-based)
-                    float left = (float)(i + 1) * pre[i].area();
-                    float right = 0.0f;
-                    const int n_right = (NB - 1) - (i + 1);
-                    if (n_right > 0) right = (float)n_right * suf[i + 1].area();
-                    const float cost = 1.0f + (left + right) / total_area;
-                    if (i == 0) { best = 0; best_cost = cost; best_nan = cost != cost; }
-                    else if (!best_nan && (cost != cost || cost < best_cost)) { best = i; best_cost = cost; best_nan = cost != cost; }
-                }
-                if (!(count > max_prims || (double)best_cost < (double)count)) leaf = true;
-                else {
-                    // partition!, Trace.jl:128-137
-                    int64_t left = t.from;
-                    for (int64_t i = t.from; i <= t.to; ++i) {
-                        if (left != i && bucket(perm[i]) <= best) { std::swap(perm[i], perm[left]); ++left; }
-                    }
-                    mid = left;
-                }
-            }
-        }
-        if (leaf) {
-            node.offset = (uint32_t)bvh->order.size();
-            node.meta = TRACE_NODE_LEAF | (uint32_t)(count < 0 ? 0 : count);
-            for (int64_t i = t.from; i <= t.to; ++i) bvh->order.push_back(perm[i]);
-            bvh->nodes.push_back(node);
-        } else {
-            node.offset = 0;
-            node.meta = (uint32_t)axis << 30;
-            bvh->nodes.push_back(node);
-            todo.push_back({mid + 1, t.to, slot});     // second child: patched into `offset` when it is emitted
-            todo.push_back({t.from, mid, -1});          // first child: emitted next, at slot + 1
-        }
-    }
-    *out = bvh;
-    return 0;
+// ------------------------------------------------------------------ parallel helpers
+// A fork-join over [0, n) in `parts` contiguous chunks on std::threads (the build runs a few hundred of these).
+template <class F>
+void parallel_chunks(int64_t n, int parts, F f) {
+    if (parts <= 1 || n < 2) { f(0, (int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve((size_t)parts - 1);
+    for (int p = 1; p < parts; ++p) th.emplace_back([=]() { f(p, n * p / parts, n * (p + 1) / parts); });
+    f(0, (int64_t)0, n / parts);
+    for (auto& t : th) t.join();
 }
 
-// Opt-in alternative (SURVEY.md §8f.2): a conventional binned SAH over the same inputs, emitted in the same node format,
-// so every kernel runs on it unchanged.  Differences from the literal build above: buckets start EMPTY, each side is
-// weighted by its primitive COUNT (cost = 1/8 + (nL*aL + nR*aR)/A), a node becomes a leaf when that is cheaper and it
-// holds <= max_node_primitives, the partition tests every element, and a degenerate split falls back to the median.
-// The closest hit of a ray does not depend on the tree (ties between equal t aside), so images agree; traversal work
-// drops because the literal cost function is degenerate (Q16: depth 42 and 2 663 empty leaves on the caustic mesh).
-extern "C" int trace_bvh_build_sah(const float* pb, int64_t n, int max_node_primitives, trace_bvh** out) {
-    if (!out || n < 0 || (n > 0 && !pb)) return 1;
-    *out = nullptr;
-    trace_bvh* bvh = new (std::nothrow) trace_bvh();
-    if (!bvh) return 2;
-    if (n == 0) { *out = bvh; return 0; }
-    const int max_prims = max_node_primitives < 1 ? 1 : (max_node_primitives < 255 ? max_node_primitives : 255);
-    const int NB = 16;
-    std::vector<float> cen((size_t)n * 3);
-    std::vector<uint32_t> perm((size_t)n);
-    for (int64_t i = 0; i < n; ++i) {
-        perm[i] = (uint32_t)i;
-        for (int k = 0; k < 3; ++k) cen[3 * i + k] = 0.5f * pb[6 * i + k] + 0.5f * pb[6 * i + 3 + k];
-    }
-    try {
-        bvh->nodes.reserve((size_t)(2 * n + 16));
-        bvh->order.reserve((size_t)n);
-    } catch (...) { delete bvh; return 2; }
-    std::vector<Task> todo;
-    todo.push_back({0, n - 1, -1});
-    while (!todo.empty()) {
-        const Task t = todo.back();
-        todo.pop_back();
-        const int64_t slot = (int64_t)bvh->nodes.size();
-        if (t.patch >= 0) bvh->nodes[t.patch].offset = (uint32_t)slot;
-        const int64_t count = t.to - t.from + 1;
-        Box all; all.reset();
-        Box cb; cb.reset();
-        for (int64_t i = t.from; i <= t.to; ++i) {
-            const float* b = pb + 6 * (size_t)perm[i];
-            all.grow(b, b + 3);
-            const float* c = &cen[3 * (size_t)perm[i]];
-            cb.grow(c, c);
-        }
-        trace_bvh_node node;
-        for (int k = 0; k < 3; ++k) { node.bmin[k] = all.lo[k]; node.bmax[k] = all.hi[k]; }
+int build_threads() {
+    const char* e = getenv("TRACE_BVH_THREADS");
+    int t = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return t < 1 ? 1 : (t > 64 ? 64 : t);
+}
+
+// Nodes with more primitives than this are split in the sequential "top" phase with their O(count) passes run in
+// parallel; smaller ones become independent subtree jobs for the thread pool.
+const int64_t kTopThreshold = 1 << 16;
+
+struct Split { bool leaf; int axis; int64_t mid; trace_bvh_node node; };
+
+// ---- the reference's split of perm[from..to] (src/accel/bvh.jl:87-185; quirks Q16).  `threads` > 1 runs the reductions
+// and the bucket evaluation in parallel: min / max reductions are exact and order-independent, and the partition's
+// swaps (whose ORDER defines the resulting permutation) stay sequential, so the tree is bit-identical to the
+// one-threaded build.
+struct LiteralSplitter {
+    const float* pb; const float* cen; uint32_t* perm; int max_prims;
+    std::vector<uint8_t>* pred;        // scratch of the top phase (n entries)
+    static const int NB = 12;
+
+    Split operator()(int64_t from, int64_t to, int threads) const {
+        Split r; r.leaf = false; r.axis = 0; r.mid = from;
+        const int64_t count = to - from + 1;
+        const int parts = (threads > 1 && count >= 32768) ? threads : 1;
+        std::vector<Box> pa((size_t)parts), pc((size_t)parts);
+        parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
+            Box all, cb; all.reset(); cb.reset();
+            for (int64_t i = from + b; i < from + e; ++i) {
+                const float* bb = pb + 6 * (size_t)perm[i]; all.grow(bb, bb + 3);
+                const float* c = &cen[3 * (size_t)perm[i]]; cb.grow(c, c);
+            }
+            pa[(size_t)p] = all; pc[(size_t)p] = cb;
+        });
+        Box all = pa[0], cb = pc[0];
+        for (int p = 1; p < parts; ++p) { all.grow(pa[(size_t)p]); cb.grow(pc[(size_t)p]); }
+        for (int k = 0; k < 3; ++k) { r.node.bmin[k] = all.lo[k]; r.node.bmax[k] = all.hi[k]; }
+        if (count == 1) { r.leaf = true; return r; }
         const int axis = cb.widest();
+        r.axis = axis;
+        if (!cb.valid() || cb.lo[axis] == cb.hi[axis]) { r.leaf = true; return r; }
+        // relative position of a centroid along `axis`, bounds.jl:134-143 (offset)
+        const bool any_extent = cb.hi[0] > cb.lo[0] || cb.hi[1] > cb.lo[1] || cb.hi[2] > cb.lo[2];
+        const float extent = cb.hi[axis] > cb.lo[axis] ? cb.hi[axis] - cb.lo[axis] : 1.0f;
+        auto bucket = [&](uint32_t prim) -> int {
+            float o = cen[3 * (size_t)prim + axis] - cb.lo[axis];
+            if (any_extent) o = o / extent;
+            int b = (int)std::floor(12.0f * o);
+            return b == NB ? NB - 1 : b;
+        };
+        if (count <= 2) {
+            // partialsort!(view, 1, by = centroid[axis]) on two entries; mid = (from + to) ÷ 2 = from
+            if (cen[3 * (size_t)perm[to] + axis] < cen[3 * (size_t)perm[from] + axis]) std::swap(perm[from], perm[to]);
+            r.mid = (from + to) / 2;
+            return r;
+        }
+        std::vector<Box> pbk((size_t)parts * NB);
+        parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
+            Box* bk = &pbk[(size_t)p * NB];
+            for (int k = 0; k < NB; ++k) bk[k].reset();
+            for (int64_t i = from + b; i < from + e; ++i) {
+                const uint32_t pr = perm[i];
+                const float* bb = pb + 6 * (size_t)pr;
+                bk[bucket(pr)].grow(bb, bb + 3);
+            }
+        });
+        Box bk[NB];
+        for (int k = 0; k < NB; ++k) { bk[k].point(0.0f); for (int p = 0; p < parts; ++p) bk[k].grow(pbk[(size_t)p * NB + k]); }
+        // prefix unions 0..i and suffix unions i..10 (bucket 11 never enters the right-hand side)
+        Box pre[NB], suf[NB];
+        pre[0] = bk[0];
+        for (int k = 1; k < NB; ++k) { pre[k] = pre[k - 1]; pre[k].grow(bk[k]); }
+        // the reference folds the right side left-to-right starting at bucket i+1; min/max are exact, so a suffix scan
+        // yields the same box
+        suf[NB - 2] = bk[NB - 2];
+        for (int k = NB - 3; k >= 0; --k) { suf[k] = bk[k]; suf[k].grow(suf[k + 1]); }
+        const float total_area = all.area();
+        int best = 0;
+        float best_cost = 0.0f;
+        bool best_nan = false;
+        for (int i = 0; i < NB - 1; ++i) {            // split after bucket i (0-based)
+            float left = (float)(i + 1) * pre[i].area();
+            float right = 0.0f;
+            const int n_right = (NB - 1) - (i + 1);
+            if (n_right > 0) right = (float)n_right * suf[i + 1].area();
+            const float cost = 1.0f + (left + right) / total_area;
+            if (i == 0) { best = 0; best_cost = cost; best_nan = cost != cost; }
+            else if (!best_nan && (cost != cost || cost < best_cost)) { best = i; best_cost = cost; best_nan = cost != cost; }
+        }
+        if (!(count > max_prims || (double)best_cost < (double)count)) { r.leaf = true; return r; }
+        // partition!, Trace.jl:128-137 (never tests the first element)
+        int64_t left = from;
+        if (parts > 1) {
+            uint8_t* pr = pred->data();
+            parallel_chunks(count, parts, [&](int, int64_t b, int64_t e) {
+                for (int64_t i = from + b; i < from + e; ++i) pr[i] = bucket(perm[i]) <= best ? 1 : 0;     // (perm[i] is still untouched when the loop below reaches i)
+            });
+            for (int64_t i = from; i <= to; ++i)
+                if (left != i && pr[i]) { std::swap(perm[i], perm[left]); ++left; }
+        } else {
+            for (int64_t i = from; i <= to; ++i)
+                if (left != i && bucket(perm[i]) <= best) { std::swap(perm[i], perm[left]); ++left; }
+        }
+        r.mid = left;
+        return r;
+    }
+};
+
+// ---- opt-in conventional binned SAH: buckets start EMPTY, each side is weighted by its primitive
+// COUNT (cost = 1/8 + (nL*aL + nR*aR)/A), a node becomes a leaf when that is cheaper and it holds <=
+// max_node_primitives, the partition tests every element, and a degenerate split falls back to the median.
+struct SahSplitter {
+    const float* pb; const float* cen; uint32_t* perm; int max_prims;
+    std::vector<uint8_t>* pred;
+    static const int NB = 16;
+
+    Split operator()(int64_t from, int64_t to, int threads) const {
+        Split r; r.leaf = false; r.axis = 0;
+        const int64_t count = to - from + 1;
+        const int parts = (threads > 1 && count >= 32768) ? threads : 1;
+        std::vector<Box> pa((size_t)parts), pc((size_t)parts);
+        parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
+            Box all, cb; all.reset(); cb.reset();
+            for (int64_t i = from + b; i < from + e; ++i) {
+                const float* bb = pb + 6 * (size_t)perm[i]; all.grow(bb, bb + 3);
+                const float* c = &cen[3 * (size_t)perm[i]]; cb.grow(c, c);
+            }
+            pa[(size_t)p] = all; pc[(size_t)p] = cb;
+        });
+        Box all = pa[0], cb = pc[0];
+        for (int p = 1; p < parts; ++p) { all.grow(pa[(size_t)p]); cb.grow(pc[(size_t)p]); }
+        for (int k = 0; k < 3; ++k) { r.node.bmin[k] = all.lo[k]; r.node.bmax[k] = all.hi[k]; }
+        const int axis = cb.widest();
+        r.axis = axis;
         bool leaf = count == 1 || !cb.valid() || !(cb.hi[axis] > cb.lo[axis]);
         if (leaf && count > max_prims && count > 1) leaf = false;        // identical centroids: split at the median
-        int64_t mid = (t.from + t.to) / 2;                                 // last index of the left side
+        int64_t mid = (from + to) / 2;                                     // last index of the left side
         if (!leaf) {
             bool split_done = false;
             if (cb.valid() && cb.hi[axis] > cb.lo[axis] && count >= 2) {
@@ -238,69 +228,241 @@ extern "C" int trace_bvh_build_sah(const float* pb, int64_t n, int max_node_prim
                     int b = (int)((cen[3 * (size_t)prim + axis] - cb.lo[axis]) * scale);
                     return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
                 };
+                std::vector<Box> pbk((size_t)parts * NB);
+                std::vector<int64_t> pcnt((size_t)parts * NB, 0);
+                parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
+                    Box* bk = &pbk[(size_t)p * NB];
+                    int64_t* cn = &pcnt[(size_t)p * NB];
+                    for (int k = 0; k < NB; ++k) bk[k].reset();
+                    for (int64_t i = from + b; i < from + e; ++i) {
+                        const uint32_t pr = perm[i];
+                        const float* bb = pb + 6 * (size_t)pr;
+                        const int k = bucket(pr);
+                        bk[k].grow(bb, bb + 3); cn[k]++;
+                    }
+                });
                 Box bk[NB];
                 int64_t cnt[NB];
-                for (int b = 0; b < NB; ++b) { bk[b].reset(); cnt[b] = 0; }
-                for (int64_t i = t.from; i <= t.to; ++i) {
-                    const uint32_t p = perm[i];
-                    const float* b = pb + 6 * (size_t)p;
-                    const int k = bucket(p);
-                    bk[k].grow(b, b + 3); cnt[k]++;
+                for (int k = 0; k < NB; ++k) {
+                    bk[k].reset(); cnt[k] = 0;
+                    for (int p = 0; p < parts; ++p) { if (pcnt[(size_t)p * NB + k]) bk[k].grow(pbk[(size_t)p * NB + k]); cnt[k] += pcnt[(size_t)p * NB + k]; }
                 }
                 float right_area[NB];
                 int64_t right_cnt[NB];
                 Box acc; acc.reset();
                 int64_t c = 0;
-                for (int b = NB - 1; b >= 1; --b) {
-                    if (cnt[b]) acc.grow(bk[b]);
-                    c += cnt[b];
-                    right_area[b] = c ? acc.area() : 0.0f; right_cnt[b] = c;
+                for (int k = NB - 1; k >= 1; --k) {
+                    if (cnt[k]) acc.grow(bk[k]);
+                    c += cnt[k];
+                    right_area[k] = c ? acc.area() : 0.0f; right_cnt[k] = c;
                 }
                 acc.reset(); c = 0;
                 const float total_area = all.area();
                 float best_cost = kInf;
                 int best = -1;
-                for (int b = 0; b < NB - 1; ++b) {                          // split after bucket b
-                    if (cnt[b]) acc.grow(bk[b]);
-                    c += cnt[b];
-                    if (c == 0 || right_cnt[b + 1] == 0) continue;
-                    const float cost = 0.125f + ((float)c * acc.area() + (float)right_cnt[b + 1] * right_area[b + 1]) /
+                for (int k = 0; k < NB - 1; ++k) {                          // split after bucket k
+                    if (cnt[k]) acc.grow(bk[k]);
+                    c += cnt[k];
+                    if (c == 0 || right_cnt[k + 1] == 0) continue;
+                    const float cost = 0.125f + ((float)c * acc.area() + (float)right_cnt[k + 1] * right_area[k + 1]) /
                                                     (total_area > 0.0f ? total_area : 1.0f);
-                    if (cost < best_cost) { best_cost = cost; best = b; }
+                    if (cost < best_cost) { best_cost = cost; best = k; }
                 }
                 if (best >= 0 && (count > max_prims || best_cost < (float)count)) {
-                    int64_t left = t.from;
-                    for (int64_t i = t.from; i <= t.to; ++i)
+                    int64_t left = from;
+                    for (int64_t i = from; i <= to; ++i)
                         if (bucket(perm[i]) <= best) { std::swap(perm[i], perm[left]); ++left; }
                     mid = left - 1;
-                    split_done = mid >= t.from && mid < t.to;
+                    split_done = mid >= from && mid < to;
                 } else if (best >= 0 || count <= max_prims) {
                     leaf = count <= max_prims;
                 }
             }
             if (!leaf && !split_done) {
                 // median split along the axis (also: two primitives, or all centroids in one bucket)
-                mid = (t.from + t.to) / 2;
-                std::nth_element(perm.begin() + t.from, perm.begin() + mid, perm.begin() + t.to + 1, [&](uint32_t a, uint32_t b) {
+                mid = (from + to) / 2;
+                std::nth_element(perm + from, perm + mid, perm + to + 1, [&](uint32_t a, uint32_t b) {
                     return cen[3 * (size_t)a + axis] < cen[3 * (size_t)b + axis];
                 });
             }
         }
-        if (leaf) {
-            node.offset = (uint32_t)bvh->order.size();
-            node.meta = TRACE_NODE_LEAF | (uint32_t)count;
-            for (int64_t i = t.from; i <= t.to; ++i) bvh->order.push_back(perm[i]);
-            bvh->nodes.push_back(node);
+        r.leaf = leaf; r.mid = mid;
+        return r;
+    }
+};
+
+struct Task { int64_t from, to; int64_t patch; };   // inclusive range into the permutation; node whose `offset` we are
+
+struct LocalTree { std::vector<trace_bvh_node> nodes; std::vector<uint32_t> order; };
+
+// sequential build of perm[from..to] into `out` with LOCAL indices (node 0 = the subtree's root, order starts at 0), nodes
+// emitted in the flattened preorder (first child = parent + 1)
+template <class Splitter>
+int build_subtree(const Splitter& split, const uint32_t* perm, int64_t from, int64_t to, LocalTree& out) {
+    std::vector<Task> todo;
+    todo.push_back({from, to, -1});
+    const int64_t node_limit = 8 * (to - from + 1) + 1024;     // a guard, never reached by terminating inputs
+    while (!todo.empty()) {
+        const Task t = todo.back();
+        todo.pop_back();
+        const int64_t slot = (int64_t)out.nodes.size();
+        if (slot > node_limit) return 3;
+        if (t.patch >= 0) out.nodes[(size_t)t.patch].offset = (uint32_t)slot;
+        Split s = split(t.from, t.to, 1);
+        const int64_t count = t.to - t.from + 1;
+        if (s.leaf) {
+            s.node.offset = (uint32_t)out.order.size();
+            s.node.meta = TRACE_NODE_LEAF | (uint32_t)(count < 0 ? 0 : count);
+            for (int64_t i = t.from; i <= t.to; ++i) out.order.push_back(perm[i]);
+            out.nodes.push_back(s.node);
         } else {
-            node.offset = 0;
-            node.meta = (uint32_t)axis << 30;
-            bvh->nodes.push_back(node);
-            todo.push_back({mid + 1, t.to, slot});
-            todo.push_back({t.from, mid, -1});
+            s.node.offset = 0;
+            s.node.meta = (uint32_t)s.axis << 30;
+            out.nodes.push_back(s.node);
+            todo.push_back({s.mid + 1, t.to, slot});     // second child: patched into `offset` when it is emitted
+            todo.push_back({t.from, s.mid, -1});          // first child: emitted next, at slot + 1
         }
     }
+    return 0;
+}
+
+// Whole build: (1) the top of the tree sequentially in preorder, each large node's passes in parallel; nodes below
+// kTopThreshold primitives are set aside as jobs; (2) the jobs in parallel (disjoint ranges of the permutation);
+// (3) stitch: item sizes -> preorder slots by a prefix sum, local indices rebased.  The result is the array the
+// one-threaded build produces, bit for bit (tests/test_bvh_build.py compares them).
+template <class Splitter>
+int build_tree(Splitter split, uint32_t* perm, int64_t n, trace_bvh* bvh) {
+    const int threads = build_threads();
+    struct Item { int kind; trace_bvh_node node; int64_t from, to; int64_t second_item; int job; };   // kind 0 interior, 1 leaf, 2 job
+    std::vector<Item> items;
+    std::vector<std::pair<int64_t, int64_t>> jobs;
+    struct TopTask { int64_t from, to; int64_t patch_item; };
+    std::vector<TopTask> todo;
+    todo.push_back({0, n - 1, -1});
+    while (!todo.empty()) {
+        const TopTask t = todo.back();
+        todo.pop_back();
+        const int64_t me = (int64_t)items.size();
+        if (t.patch_item >= 0) items[(size_t)t.patch_item].second_item = me;
+        const int64_t count = t.to - t.from + 1;
+        if (threads == 1 ? false : count <= kTopThreshold) {
+            items.push_back({2, trace_bvh_node(), t.from, t.to, -1, (int)jobs.size()});
+            jobs.push_back({t.from, t.to});
+            continue;
+        }
+        if (threads == 1 && me == 0) {          // one thread: the plain sequential build of the whole range
+            items.push_back({2, trace_bvh_node(), t.from, t.to, -1, 0});
+            jobs.push_back({t.from, t.to});
+            continue;
+        }
+        Split s = split(t.from, t.to, threads);
+        if (s.leaf) {
+            s.node.meta = TRACE_NODE_LEAF | (uint32_t)count;
+            items.push_back({1, s.node, t.from, t.to, -1, -1});
+        } else {
+            s.node.meta = (uint32_t)s.axis << 30;
+            items.push_back({0, s.node, t.from, t.to, -1, -1});
+            todo.push_back({s.mid + 1, t.to, me});
+            todo.push_back({t.from, s.mid, -1});
+        }
+    }
+    std::vector<LocalTree> local(jobs.size());
+    std::vector<int> rcs(jobs.size(), 0);
+    {
+        std::atomic<size_t> next(0);
+        auto worker = [&]() {
+            for (;;) {
+                const size_t j = next.fetch_add(1);
+                if (j >= jobs.size()) break;
+                const int64_t cnt = jobs[j].second - jobs[j].first + 1;
+                local[j].nodes.reserve((size_t)(2 * cnt + 16));
+                local[j].order.reserve((size_t)cnt);
+                rcs[j] = build_subtree(split, perm, jobs[j].first, jobs[j].second, local[j]);
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, jobs.size()));
+        std::vector<std::thread> th;
+        for (int k = 1; k < nt; ++k) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
+    }
+    for (int rc : rcs) if (rc) return rc;
+    // stitch
+    std::vector<int64_t> node_base(items.size() + 1, 0), order_base(items.size() + 1, 0);
+    for (size_t i = 0; i < items.size(); ++i) {
+        const Item& it = items[i];
+        node_base[i + 1] = node_base[i] + (it.kind == 2 ? (int64_t)local[(size_t)it.job].nodes.size() : 1);
+        order_base[i + 1] = order_base[i] + (it.kind == 2 ? (int64_t)local[(size_t)it.job].order.size() : (it.kind == 1 ? it.to - it.from + 1 : 0));
+    }
+    if (node_base.back() > 0x7fffffffll) return 4;
+    bvh->nodes.resize((size_t)node_base.back());
+    bvh->order.resize((size_t)order_base.back());
+    parallel_chunks((int64_t)items.size(), threads, [&](int, int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; ++i) {
+            const Item& it = items[(size_t)i];
+            if (it.kind == 0) {
+                trace_bvh_node nd = it.node;
+                nd.offset = (uint32_t)node_base[(size_t)it.second_item];
+                bvh->nodes[(size_t)node_base[(size_t)i]] = nd;
+            } else if (it.kind == 1) {
+                trace_bvh_node nd = it.node;
+                nd.offset = (uint32_t)order_base[(size_t)i];
+                bvh->nodes[(size_t)node_base[(size_t)i]] = nd;
+                for (int64_t k = it.from; k <= it.to; ++k) bvh->order[(size_t)(order_base[(size_t)i] + k - it.from)] = perm[k];
+            } else {
+                const LocalTree& lt = local[(size_t)it.job];
+                const uint32_t nb = (uint32_t)node_base[(size_t)i], ob = (uint32_t)order_base[(size_t)i];
+                for (size_t k = 0; k < lt.nodes.size(); ++k) {
+                    trace_bvh_node nd = lt.nodes[k];
+                    nd.offset += (nd.meta >> 30) == 3 ? ob : nb;
+                    bvh->nodes[(size_t)nb + k] = nd;
+                }
+                if (!lt.order.empty()) memcpy(&bvh->order[(size_t)ob], lt.order.data(), lt.order.size() * sizeof(uint32_t));
+            }
+        }
+    });
+    return 0;
+}
+
+template <class Splitter>
+int build_entry(const float* pb, int64_t n, int max_prims, trace_bvh** out) {
+    if (!out || n < 0 || (n > 0 && !pb)) return 1;
+    *out = nullptr;
+    if (n >= 0x40000000ll) return 1;
+    trace_bvh* bvh = new (std::nothrow) trace_bvh();
+    if (!bvh) return 2;
+    if (n == 0) { *out = bvh; return 0; }
+    try {
+        std::vector<float> cen((size_t)n * 3);
+        std::vector<uint32_t> perm((size_t)n);
+        std::vector<uint8_t> pred((size_t)n);
+        parallel_chunks(n, build_threads(), [&](int, int64_t b, int64_t e) {
+            for (int64_t i = b; i < e; ++i) {
+                perm[(size_t)i] = (uint32_t)i;
+                for (int k = 0; k < 3; ++k) cen[3 * (size_t)i + k] = 0.5f * pb[6 * i + k] + 0.5f * pb[6 * i + 3 + k];
+            }
+        });
+        Splitter split{pb, cen.data(), perm.data(), max_prims, &pred};
+        const int rc = build_tree(split, perm.data(), n, bvh);
+        if (rc) { delete bvh; return rc; }
+    } catch (...) { delete bvh; return 2; }
     *out = bvh;
     return 0;
+}
+
+}  // namespace
+
+extern "C" int trace_bvh_build(const float* pb, int64_t n, int max_node_primitives, trace_bvh** out) {
+    return build_entry<LiteralSplitter>(pb, n, max_node_primitives < 255 ? max_node_primitives : 255, out);
+}
+
+// Opt-in alternative (SURVEY.md §8f.2): a conventional binned SAH over the same inputs, emitted in the same node format,
+// so every kernel runs on it unchanged.  The closest hit of a ray does not depend on the tree (ties between equal t
+// aside), so images agree; traversal work drops because the literal cost function is degenerate (Q16: depth 42 and
+// 2 663 empty leaves on the caustic mesh).
+extern "C" int trace_bvh_build_sah(const float* pb, int64_t n, int max_node_primitives, trace_bvh** out) {
+    const int m = max_node_primitives < 1 ? 1 : (max_node_primitives < 255 ? max_node_primitives : 255);
+    return build_entry<SahSplitter>(pb, n, m, out);
 }
 
 extern "C" int64_t trace_bvh_num_nodes(const trace_bvh* b) { return b ? (int64_t)b->nodes.size() : 0; }

@@ -57,7 +57,7 @@ struct trace_ctx {
     int fuse_primary = 1;         // Whitted: generate + trace the camera rays in one kernel (no primary-ray queue)
     int cur_level = 0;            // bounce level of the extend launch being enqueued (set by the integrators)
     int work_slot = 0;
-    int leaf_wait = 0;            // 0: plain traversal loop; 4/8/16/32: warp-synchronous loop with batched leaves (traverse.cuh)
+    int leaf_wait = -1;           // walk selector: -1 pair nodes (default, option "walk" 1), 0 the reference loop ("walk" 0), 4/8/16/32 batched leaves
     int time_kernels = 0;
     int rank = 0, world = 1;
     void* comm = nullptr;         // ncclComm_t of this rank (comm.cpp), null until trace_comm_init
@@ -120,8 +120,10 @@ struct trace_ctx {
                     fprintf(tl, "%d %d %.4f %.4f\n", kev[i].lane, kev[i].kind, t0, t1);
             }
             if (cudaEventElapsedTime(&ms, kev[i].a, kev[i].b) == cudaSuccess) {
-                if (kev[i].kind == 0) { stats.ms_extend += ms; stats.extend_launches++; }
-                else { stats.ms_shadow += ms; stats.shadow_launches++; }
+                const int k = kev[i].kind;
+                if (k == TRACE_K_EXTEND) { stats.ms_extend += ms; stats.extend_launches++; }
+                else if (k == TRACE_K_SHADOW) { stats.ms_shadow += ms; stats.shadow_launches++; }
+                if (k >= 0 && k < TRACE_K_COUNT) { stats.ms_kind[k] += ms; stats.launches_kind[k]++; }
             }
         }
         if (tl) fclose(tl);
@@ -149,7 +151,7 @@ struct trace_ctx {
     } while (0)
 
 // u64 device stats block layout (ctx->b_counters, after the int counters)
-enum { ST_RAYS_EXTEND = 0, ST_RAYS_SHADOW = 1, ST_NODES = 2, ST_PRIMS = 3, ST_DEPOSITS = 4, ST_COUNT = 8 };
+enum { ST_RAYS_EXTEND = 0, ST_RAYS_SHADOW = 1, ST_NODES = 2, ST_PRIMS = 3, ST_DEPOSITS = 4, ST_CANDIDATES = 5, ST_REQUESTS = 6, ST_GRID_ITEMS = 7, ST_PRIMARY_RAYS = 8, ST_PRIMARY_HITS = 9, ST_COUNT = 12 };
 static const int TR_INT_COUNTERS = 128;    // ints at the start of b_counters (64..127: work counters of persistent launches)
 // int counter slots: [1 .. TR_MAX_DEPTH] ray-queue length per bounce level, [32] shadow / deposit-request queue
 enum { IC_OVERFLOW = 60, IC_ERROR = 61, IC_OVERFLOW_SHADOW = 62, IC_OVERFLOW_DEPOSIT = 63 };
@@ -230,4 +232,5 @@ int comm_allgather(trace_ctx* ctx, const float* send, float* recv, size_t send_c
 int whitted_render_device(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film, int spp, int max_depth,
                           uint64_t seed, float* film_xyzw_device);
 void sppm_free(trace_ctx* ctx);
+void sppm_end_session(trace_ctx* ctx);
 void whitted_film_range(const trace_ctx* ctx, long long npix, long long* p0, long long* p1);

@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(unsigned int* data, int
 __global__ void k_grid_check(SppmLaunch L) {
     if (L.grid->total_items > L.items_cap) L.flags[IC_OVERFLOW] = 1;
     L.cell_start[L.npix] = L.grid->total_items;
+    atomicAdd(&L.stats[ST_GRID_ITEMS], (unsigned long long)L.grid->total_items);
 }
 
 // ---------------------------------------------------------------- photon pass (sppm.jl:320-436)
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(128) k_photon_deposit(SppmLaunch L, int level)
     const int n = min(L.counters[32], L.cap_shadow);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    unsigned int deposits = 0;
+    unsigned int deposits = 0, candidates = 0;
     // TR_DEPOSIT_SPLIT warps share one request (interleaved 32-entry slices of its list): a request's chain of
     // dependent gathers is 8x shorter and there are 8x more independent tasks to hide latency with
     const long long n_tasks = (long long)n * TR_DEPOSIT_SPLIT;
@@ -418,6 +419,7 @@ __global__ void __launch_bounds__(128) k_photon_deposit(SppmLaunch L, int level)
         const float3 wo = xyz(L.sd[r]), beta = xyz(L.sc_contrib[r]);
         for (unsigned int e = e0 + sub * 32 + lane; e < e1; e += 32 * TR_DEPOSIT_SPLIT) {
             const float4 A = __ldcs(&L.cell_vp[e]);                  // streamed once per request: keep it out of L1
+            candidates++;
             const float3 dd = xyz(A) - p;
             if (dot3(dd, dd) > A.w) continue;
             const unsigned int pix = L.cell_items[e];
@@ -432,8 +434,9 @@ __global__ void __launch_bounds__(128) k_photon_deposit(SppmLaunch L, int level)
             deposits++;
         }
     }
-    for (int off = 16; off > 0; off >>= 1) deposits += __shfl_xor_sync(0xffffffffu, deposits, off);
+    for (int off = 16; off > 0; off >>= 1) { deposits += __shfl_xor_sync(0xffffffffu, deposits, off); candidates += __shfl_xor_sync(0xffffffffu, candidates, off); }
     if (lane == 0 && deposits) atomicAdd(&L.stats[ST_DEPOSITS], (unsigned long long)deposits);
+    if (lane == 0 && candidates) atomicAdd(&L.stats[ST_CANDIDATES], (unsigned long long)candidates);
 }
 
 // ---------------------------------------------------------------- per-iteration update and image (sppm.jl:438-472)
@@ -490,6 +493,7 @@ __global__ void k_sppm_stats(int* counters, unsigned long long* stats, int max_d
         s = counters[32];
         atomicAdd(&stats[ST_RAYS_EXTEND], e);              // (lanes run concurrently)
         if (count_shadow) atomicAdd(&stats[ST_RAYS_SHADOW], s);      // in the photon pass slots 32.. count deposit requests
+        else atomicAdd(&stats[ST_REQUESTS], s);
     }
 }
 
@@ -511,7 +515,7 @@ struct SppmState {
     bool active = false;
 };
 
-void sppm_free(trace_ctx* c) {
+void sppm_free(trace_ctx* c) {                 // releases the device memory too (trace_destroy)
     if (!c->sppm) return;
     SppmState* s = c->sppm;
     for (auto& b : s->pix) b.release();
@@ -523,6 +527,11 @@ void sppm_free(trace_ctx* c) {
     s->grid.release(); s->scan_sums.release(); s->table.release(); s->lights.release();
     delete s;
     c->sppm = nullptr;
+}
+// ends a session but keeps the (grow-only) buffers: a caller rendering frame after frame (docs/code/caustic_moving.jl:
+// 51 frames) does not pay ~1 GB of cudaMalloc / cudaFree per trace_render_sppm
+void sppm_end_session(trace_ctx* c) {
+    if (c->sppm) { c->sppm->active = false; c->sppm->traced_it = -1; }
 }
 
 static float host_luminance_power(const trace_ctx*, const DeviceLight& l) {       // to_Y(power(light)), sppm.jl:564-569
@@ -544,15 +553,16 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     if (max_depth < 1 || max_depth > TR_MAX_DEPTH) return c->fail("trace_sppm_begin: max_depth must be in [1, %d]", TR_MAX_DEPTH);
     if (!(r0 > 0.0f)) return c->fail("trace_sppm_begin: bad radius");
     if (c->scene.n_lights < 1) return c->fail("trace_sppm_begin: the scene has no lights");
-    sppm_free(c);
-    SppmState* s = new SppmState();
-    c->sppm = s;
+    sppm_end_session(c);
+    if (!c->sppm) c->sppm = new SppmState();
+    SppmState* s = c->sppm;
     SppmLaunch& L = s->L;
+    memset(&L, 0, sizeof(L));
     L.sc = c->scene;
     ctx_device_camera(cam, &L.cam);
     if (ctx_device_film(c, film, &L.film, &s->table)) return 1;
     L.W = L.film.width; L.H = L.film.height; L.npix = L.W * L.H;
-    if (c->rank < 0 || c->rank >= c->world) { sppm_free(c); return c->fail("rank %d outside world %d", c->rank, c->world); }
+    if (c->rank < 0 || c->rank >= c->world) return c->fail("rank %d outside world %d", c->rank, c->world);
     L.world = c->world; L.rank = c->rank;
     L.chunk_rows = (L.H + L.world - 1) / L.world;
     L.nstore = L.world * L.chunk_rows * L.W;
@@ -584,8 +594,8 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     // costs every ray ~1000 node visits), not bound by a few slow rays (profiles/r1_experiments.md)
     const int K = c->sppm_lanes > 0 ? c->sppm_lanes : 1;
     s->Kc = s->Kp = std::min(K, trace_ctx::MAX_LANES / 2);
-    TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_ph_fork, cudaEventDisableTiming));
-    TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_grid, cudaEventDisableTiming));
+    if (!s->ev_ph_fork) TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_ph_fork, cudaEventDisableTiming));
+    if (!s->ev_grid) TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_grid, cudaEventDisableTiming));
     // camera queues hold this rank's pixels, photon queues one chunk of photons; both are cut evenly over the lanes
     const size_t rank_slots = (size_t)L.chunk_rows * L.W;
     const size_t cam_cap = (rank_slots + s->Kc - 1) / s->Kc;
@@ -622,7 +632,7 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     std::vector<float> func((size_t)nl), cdf((size_t)nl + 1);
     for (int i = 0; i < nl; ++i) {
         // the reference defines no sample_le for DirectionalLight (lights/directional.jl): its photon pass would throw
-        if (hl[i].kind == TRACE_LIGHT_DIRECTIONAL) { sppm_free(c); return c->fail("SPPM: DirectionalLight cannot emit photons (no sample_le in the reference)"); }
+        if (hl[i].kind == TRACE_LIGHT_DIRECTIONAL) { return c->fail("SPPM: DirectionalLight cannot emit photons (no sample_le in the reference)"); }
         func[i] = host_luminance_power(c, hl[i]);
     }
     cdf[0] = 0.0f;
@@ -679,14 +689,18 @@ static int sppm_camera_lane(trace_ctx* c, SppmState* s, int l, int iteration) {
     TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), st));
     TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), st)); c->work_slot = 0;
     const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
+    c->kev_begin(TRACE_K_GENERATE);
     k_sppm_cam_generate<<<g_stream, 256, 0, st>>>(W);
+    c->kev_end();
     c->stats.kernel_launches++;
     for (int level = 1; level <= W.max_depth; ++level) {
         const int cur = (level - 1) & 1;
         c->cur_level = level;
         launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
                       stats + ST_NODES, W.flags + IC_ERROR);
+        c->kev_begin(TRACE_K_SHADE);
         k_sppm_cam_shade<<<occupancy_grid(c, k_sppm_cam_shade, 128), 128, 0, st>>>(W, level);
+        c->kev_end();
         c->stats.kernel_launches++;
     }
     // shadow rays of all levels in one any-hit launch (they only feed Ld)
@@ -697,7 +711,8 @@ static int sppm_camera_lane(trace_ctx* c, SppmState* s, int l, int iteration) {
     return 0;
 }
 
-extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
+// camera pass of this rank's rows, enqueued only (no host wait)
+static int sppm_camera_pass_async(trace_ctx* c, int iteration) {
     if (!c) return 1;
     cudaSetDevice(c->device);
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_camera_pass: call trace_sppm_begin first");
@@ -717,12 +732,23 @@ extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
         }
     }
     TR_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+static int sppm_build_grid_async(trace_ctx* c);
+
+extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
+    if (sppm_camera_pass_async(c, iteration)) return 1;
     if (c->world > 1) return check_flags(c, "trace_sppm_camera_pass");   // caller all-gathers the visible points, then build_grid
     return trace_sppm_build_grid(c);
 }
 
 // hash grid of the visible points (sppm.jl:272-318): bounds -> resolution -> count -> scan -> fill
 extern "C" int trace_sppm_build_grid(trace_ctx* c) {
+    if (sppm_build_grid_async(c)) return 1;
+    return check_flags(c, "trace_sppm_build_grid");
+}
+static int sppm_build_grid_async(trace_ctx* c) {
     if (!c) return 1;
     cudaSetDevice(c->device);
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_build_grid: call trace_sppm_begin first");
@@ -731,6 +757,7 @@ extern "C" int trace_sppm_build_grid(trace_ctx* c) {
     const int g_stream = persistent_grid(c, 8);
     const int n_cells = L.npix + 1;
     const int scan_blocks = (n_cells + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
+    c->kev_begin(TRACE_K_GRID);                                 // (the ten launches of the grid build are timed as one)
     k_grid_reset<<<1, 1, 0, c->stream>>>(L.grid);
     k_grid_bounds<<<g_stream, 256, 0, c->stream>>>(L);
     k_grid_params<<<1, 1, 0, c->stream>>>(L.grid);
@@ -741,9 +768,10 @@ extern "C" int trace_sppm_build_grid(trace_ctx* c) {
     k_scan_add<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(L.cell_start, n_cells, s->scan_sums.as<unsigned int>(), L.cell_cursor);
     k_grid_check<<<1, 1, 0, c->stream>>>(L);
     k_grid_insert<true><<<g_stream, 256, 0, c->stream>>>(L);
+    c->kev_end();
     c->stats.kernel_launches += 10;
     TR_CUDA(c, cudaGetLastError());
-    return check_flags(c, "trace_sppm_build_grid");
+    return 0;
 }
 
 // Photon tracing of [begin, end) on the photon lanes: generate -> (extend -> shade) x depth.  The shade kernel leaves
@@ -759,14 +787,18 @@ static int sppm_trace_lane(trace_ctx* c, SppmState* s, int j, int iteration, int
     TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), st));
     TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), st)); c->work_slot = 0;
     const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
+    c->kev_begin(TRACE_K_GENERATE);
     k_photon_generate<<<g_stream, 256, 0, st>>>(W);
+    c->kev_end();
     c->stats.kernel_launches++;
     for (int level = 1; level <= W.max_depth; ++level) {
         const int cur = (level - 1) & 1;
         c->cur_level = level;
         launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
                       stats + ST_NODES, W.flags + IC_ERROR);
+        c->kev_begin(TRACE_K_SHADE);
         k_photon_shade<<<occupancy_grid(c, k_photon_shade, 128), 128, 0, st>>>(W, level);
+        c->kev_end();
         c->stats.kernel_launches++;
     }
     return 0;
@@ -776,7 +808,9 @@ static int sppm_deposit_lane(trace_ctx* c, SppmState* s, int j) {
     SppmLaunch& W = s->ph_lane[j];
     cudaStream_t st = c->cur_stream;
     // deposit requests of all bounce levels in one launch (deposits do not feed back into the photon paths)
+    c->kev_begin(TRACE_K_DEPOSIT);
     k_photon_deposit<<<occupancy_grid(c, k_photon_deposit, 128), 128, 0, st>>>(W, 0);
+    c->kev_end();
     k_sppm_stats<<<1, 32, 0, st>>>(W.counters, ctx_stats64(c), W.max_depth, W.cap, 0);
     c->stats.kernel_launches += 2;
     return 0;
@@ -862,7 +896,9 @@ extern "C" int trace_sppm_update(trace_ctx* c) {
     if (!c) return 1;
     cudaSetDevice(c->device);
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_update: call trace_sppm_begin first");
+    c->kev_begin(TRACE_K_UPDATE);
     k_sppm_update<<<persistent_grid(c, 4), 256, 0, c->stream>>>(c->sppm->L);
+    c->kev_end();
     c->stats.kernel_launches++;
     TR_CUDA(c, cudaGetLastError());
     return 0;
@@ -876,6 +912,11 @@ extern "C" int trace_sppm_image(trace_ctx* c, int iteration, float* rgb_out) {
     SppmLaunch& L = c->sppm->L;
     const size_t bytes = (size_t)L.npix * 3 * sizeof(float);
     TR_CUDA(c, c->b_misc[6].ensure(bytes));
+    if (c->comm && c->world > 1) {       // Ld is accumulated only by the rank that owns the row: gather it (idempotent)
+        const size_t slice = (size_t)L.nstore / (size_t)c->world * 4;
+        float* base = reinterpret_cast<float*>(L.Ld);
+        if (comm_allgather(c, base + (size_t)c->rank * slice, base, slice)) return 1;
+    }
     k_sppm_image<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L, iteration, c->b_misc[6].as<float>());
     c->stats.kernel_launches++;
     TR_CUDA(c, cudaMemcpyAsync(rgb_out, c->b_misc[6].p, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -887,8 +928,33 @@ extern "C" int trace_sppm_end(trace_ctx* c) {
     if (!c) return 1;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    sppm_free(c);
+    sppm_end_session(c);
     return 0;
+}
+
+// One SPPM iteration (sppm.jl:153-165) enqueued on the context's streams without any host wait.  With a communicator
+// the two exchange steps of SURVEY.md 8e run here: all-gather of the visible points (camera paths are sharded by image
+// rows) and all-reduce(sum) of (Phi, M) (photons are sharded by index range).
+static int sppm_iteration_async(trace_ctx* c, int it) {
+    SppmState* s = c->sppm;
+    SppmLaunch& L = s->L;
+    const bool multi = c->comm != nullptr && c->world > 1;
+    const int64_t P = L.photons_per_iteration;
+    const int64_t b = multi ? P * c->rank / c->world : 0, e = multi ? P * (c->rank + 1) / c->world : P;
+    // photon tracing first: it does not need the grid and overlaps the camera pass (and the all-gather) on its own stream
+    if (trace_sppm_trace_photons(c, it, b, e) || sppm_camera_pass_async(c, it)) return 1;
+    if (multi) {
+        // rank r owns slice r of every per-pixel array (storage order): five in-place all-gathers of the visible points
+        const size_t slice = (size_t)L.nstore / (size_t)c->world * 4;
+        float4* arr[5] = {L.vpA, L.vpB, L.vpC, L.vpD, L.vpE};
+        for (int k = 0; k < 5; ++k) {
+            float* base = reinterpret_cast<float*>(arr[k]);
+            if (comm_allgather(c, base + (size_t)c->rank * slice, base, slice)) return 1;
+        }
+    }
+    if (sppm_build_grid_async(c) || trace_sppm_photon_pass(c, it, b, e)) return 1;
+    if (multi && comm_allreduce_sum(c, reinterpret_cast<float*>(L.flux), (size_t)L.nstore * 4)) return 1;
+    return trace_sppm_update(c);
 }
 
 extern "C" int trace_render_sppm(trace_ctx* c, const trace_camera* cam, const trace_film_desc* film, float r0, int max_depth,
@@ -897,25 +963,36 @@ extern "C" int trace_render_sppm(trace_ctx* c, const trace_camera* cam, const tr
     if (!c) return 1;
     if (n_iterations < 1) return c->fail("trace_render_sppm: n_iterations must be >= 1");
     if (!rgb_out) return c->fail("trace_render_sppm: null output");
+    if (c->world != 1 && !c->comm)
+        return c->fail("trace_render_sppm over several ranks needs trace_comm_init (or drive the stepwise trace_sppm_* API and do the exchanges yourself)");
     if (trace_sppm_begin(c, cam, film, r0, max_depth, photons, seed)) return 1;
-    const int64_t P = c->sppm->L.photons_per_iteration;
-    // photon range of this rank (world > 1 needs the caller to all-reduce the flux buffer: use the stepwise API)
-    if (c->world != 1) { sppm_free(c); return c->fail("trace_render_sppm is single-GPU; use the stepwise trace_sppm_* API to shard photons"); }
     TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     for (int it = 1; it <= n_iterations; ++it) {
-        // photon tracing first: it is asynchronous and overlaps the camera pass (whose grid build ends with a host check)
-        if (trace_sppm_trace_photons(c, it, 0, P) || trace_sppm_camera_pass(c, it) || trace_sppm_photon_pass(c, it, 0, P) ||
-            trace_sppm_update(c)) { sppm_free(c); return 1; }
+        if (sppm_iteration_async(c, it)) { sppm_end_session(c); return 1; }
         if (on_image && write_frequency > 0 && (it % write_frequency == 0) && it != n_iterations) {   // sppm.jl:167-171
-            if (trace_sppm_image(c, it, rgb_out)) { sppm_free(c); return 1; }
+            if (trace_sppm_image(c, it, rgb_out)) { sppm_end_session(c); return 1; }
             on_image(user, it, rgb_out);
         }
     }
     TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    if (trace_sppm_image(c, n_iterations, rgb_out)) { sppm_free(c); return 1; }
+    if (trace_sppm_image(c, n_iterations, rgb_out)) { sppm_end_session(c); return 1; }      // (the one host wait; checks the error flags)
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->stats.ms_total = ms;
     if (on_image) on_image(user, n_iterations, rgb_out);
     return trace_sppm_end(c);
+}
+
+// Session form of the same loop for callers that keep iterating (animations, benchmarks): trace_sppm_begin, then
+// trace_sppm_iterate(n) as often as wanted - n iterations are enqueued back to back, no host wait - then trace_sppm_image
+// / trace_sppm_end.  Collectives as in trace_render_sppm when a communicator exists.
+extern "C" int trace_sppm_iterate(trace_ctx* c, int first_iteration, int n) {
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_iterate: call trace_sppm_begin first");
+    if (first_iteration < 1 || n < 0) return c->fail("trace_sppm_iterate: bad arguments");
+    if (c->world != 1 && !c->comm) return c->fail("trace_sppm_iterate over several ranks needs trace_comm_init");
+    for (int it = first_iteration; it < first_iteration + n; ++it)
+        if (sppm_iteration_async(c, it)) return 1;
+    return 0;
 }

@@ -17,6 +17,8 @@ struct RayPrep {            // quantities that depend on the ray only
     int kz;                 // permutation of the triangle test
     float Sx, Sy, Sz;       // shear
     float mx, my, mz;       // SLAB 2: per-axis slack of the conservative interval, in units of t
+    float mmax;             // max(mx, my, mz)
+    bool any_zero;          // a direction component is 0: 1/d is Inf, slab products may be NaN - no shortcuts for this ray
 };
 
 // Spatial slack of the conservative box test (SLAB 2), relative to the largest coordinate in play: 2^-17 ~ 7.6e-6,
@@ -49,6 +51,8 @@ __device__ __forceinline__ RayPrep prepare_ray(float3 o, float3 d, float scene_s
     r.Sx = -dx * denom; r.Sy = -dy * denom; r.Sz = denom;
     const float slack = TR_GUARD_REL * fmaxf(scene_scale, fmaxf(fabsf(o.x), fmaxf(fabsf(o.y), fabsf(o.z))));
     r.mx = slack * fabsf(r.inv.x); r.my = slack * fabsf(r.inv.y); r.mz = slack * fabsf(r.inv.z);
+    r.mmax = fmaxf(r.mx, fmaxf(r.my, r.mz));
+    r.any_zero = (d.x == 0.0f) | (d.y == 0.0f) | (d.z == 0.0f);
     return r;
 }
 
@@ -320,6 +324,45 @@ __device__ __forceinline__ bool slab_child(const float4 n0, const float4 n1, con
     return ok;               // the caller adds the one t_max-dependent condition: tx_min < t_max
 }
 
+// Fast three-way classification of one child's box test (SLAB 2 only).  With a0 = entry and a1 = exit distances of the
+// three slabs (the same six products the reference forms), t_enter = max a0 and t_exit = min a1 (no NaN in play):
+//   * ACCEPT when t_enter <= t_exit and t_exit > 0 - the textbook test on the reference's own numbers.  Every rejecting
+//     comparison of the reference's test (bounds.jl:186-199, incl. the loose y far bound) implies t_enter > t_exit or
+//     t_exit <= 0, so the reference accepts too, with tx_min == t_enter; the guard's interval is this one widened, so it
+//     accepts as well.  Hence exactly what slab_child<2> returns.
+//   * REJECT when the interval is empty by more than twice the largest slack, or ends before -slack: then the guard's
+//     widened interval is empty / behind the origin as well, and slab_child<2> returns false (not used below analytic
+//     spheres, where the guard is off).
+//   * otherwise UNDECIDED (grazing within the slack band, NaN boxes): the caller evaluates slab_child<2> in full.
+// About 26 instructions per child instead of 44; the undecided band is a few rays in a million box tests.
+__device__ __forceinline__ void slab_child_fast(const float4 n0, const float4 n1, const RayPrep& r, float& t_enter_out, bool& accept, bool& reject) {
+    const float ax0 = ((r.nx ? n0.w : n0.x) - r.o.x) * r.inv.x;
+    const float ax1 = ((r.nx ? n0.x : n0.w) - r.o.x) * r.inv.x;
+    const float ay0 = ((r.ny ? n1.x : n0.y) - r.o.y) * r.inv.y;
+    const float ay1 = ((r.ny ? n0.y : n1.x) - r.o.y) * r.inv.y;
+    const float az0 = ((r.nz ? n1.y : n0.z) - r.o.z) * r.inv.z;
+    const float az1 = ((r.nz ? n0.z : n1.y) - r.o.z) * r.inv.z;
+    const float t_enter = fmaxf(fmaxf(ax0, ay0), az0);
+    const float t_exit = fminf(fminf(ax1, ay1), az1);
+    accept = (t_enter <= t_exit) & (t_exit > 0.0f);
+    reject = (((t_enter - t_exit) > 2.0f * r.mmax) | (t_exit < -r.mmax)) & ((__float_as_uint(n1.z) & TR_REF_SPHERE_BELOW) == 0u);
+    t_enter_out = t_enter;
+}
+
+// both children of a pair: static verdicts s0, s1 and entry distances t0, t1 (see slab_child)
+template <int SLAB>
+__device__ __forceinline__ void slab_children(const float4 q0, const float4 q1, const float4 q2, const float4 q3, const RayPrep& r,
+                                              bool& s0, bool& s1, float& t0, float& t1) {
+    if (SLAB == 2) {
+        bool a0, r0, a1, r1;
+        slab_child_fast(q0, q1, r, t0, a0, r0);
+        slab_child_fast(q2, q3, r, t1, a1, r1);
+        if (!r.any_zero & (a0 | r0) & (a1 | r1)) { s0 = a0; s1 = a1; return; }
+    }
+    s0 = slab_child<SLAB>(q0, q1, r, t0);
+    s1 = slab_child<SLAB>(q2, q3, r, t1);
+}
+
 template <int SLAB, bool ANY, bool COUNT>
 __device__ __forceinline__ bool traverse_pair(const DeviceScene& sc, float3 o, float3 d, float tmax, HitRecord& out,
                                               unsigned long long* counters, int* error_flag) {
@@ -373,8 +416,8 @@ __device__ __forceinline__ bool traverse_pair(const DeviceScene& sc, float3 o, f
             const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
             if (COUNT) n_nodes += 2;
             float t0, t1;
-            const bool s0 = slab_child<SLAB>(q0, q1, r, t0);
-            const bool s1 = slab_child<SLAB>(q2, q3, r, t1);
+            bool s0, s1;
+            slab_children<SLAB>(q0, q1, q2, q3, r, s0, s1, t0, t1);
             const bool neg = (signs >> (__float_as_uint(q1.w) & 3u)) & 1u;      // near child = second child iff d[axis] < 0
             const uint32_t ref0 = __float_as_uint(q1.z), ref1 = __float_as_uint(q3.z);
             const float near_t = neg ? t1 : t0, far_t = neg ? t0 : t1;
@@ -509,117 +552,3 @@ __device__ __forceinline__ bool traverse_any(const DeviceScene& sc, bool valid, 
     } else return traverse_lb<SLAB, ANY, COUNT, (WAIT > 0 ? WAIT : 1), TR_PARK_MAX>(sc, valid, o, d, tmax, out, counters, error_flag);
 }
 
-// ------------------------------------------------------------------ persistent warps with dynamic ray fetch
-// The plain kernels give each thread a fixed slice of the queue; a warp then runs until its SLOWEST ray is done
-// (ncu, pair walk: 28 of 32 lanes enter the box tests on coherent primary rays, but only 23 / 19 on the rays of bounce
-// levels 2 / 3 and 23 on shadow rays).  Here a warp keeps walking and, whenever at least TR_REFILL_LANES of its lanes
-// are idle, those lanes claim the next rays of the queue from a device-side counter (one warp-aggregated atomic) -
-// the "persistent threads + dynamic fetch" scheme of Aila & Laine.  Each lane runs exactly the steps of
-// traverse_pair<>() on its ray, so per-ray results are unchanged.  Used for the incoherent launches (bounce levels
-// >= 2, shadow rays), where the tails are long and there is little coherence to lose by mixing rays in a warp.
-#ifndef TR_REFILL_LANES
-#define TR_REFILL_LANES 12
-#endif
-
-template <int SLAB, bool ANY, class Finish>
-__device__ __forceinline__ void trace_persistent(const DeviceScene& sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
-                                                 int n, int* work_counter, int* error_flag, Finish finish) {
-    const unsigned full = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    bool have = false, exhausted = false;
-    int ray = 0;
-    RayPrep r;
-    float tmax = 0.0f;
-    uint32_t item = 0;
-    int sp = 0;
-    uint2 tos = make_uint2(0u, 0u);
-    uint2 stack[TR_STACK_SIZE];
-    unsigned signs = 0;
-    HitRecord out;
-    out.prim = 0; out.t = 0.0f; out.b0 = 0.0f; out.b1 = 0.0f;
-    const bool cull_far = sc.n_spheres == 0;
-    if (sc.n_nodes == 0) n = 0;
-    for (;;) {
-        const unsigned idle = __ballot_sync(full, !have);
-        if (idle != 0u) {
-            if (!exhausted && (__popc(idle) >= TR_REFILL_LANES || idle == full)) {
-                int base = 0;
-                const int want = __popc(idle);
-                const int leader = __ffs(idle) - 1;
-                if ((int)lane == leader) base = atomicAdd(work_counter, want);
-                base = __shfl_sync(full, base, leader);
-                if (base + want >= n) exhausted = true;
-                const int mine = base + __popc(idle & lt_mask);
-                if (!have && mine < n) {
-                    const float4 o4 = ro[mine], d4 = rd[mine];
-                    r = prepare_ray(xyz(o4), xyz(d4), sc.scene_scale);
-                    tmax = o4.w; ray = mine; sp = 0;
-                    out.prim = 0; out.t = tmax; out.b0 = 0.0f; out.b1 = 0.0f;
-                    signs = (r.nx ? 1u : 0u) | (r.ny ? 2u : 0u) | (r.nz ? 4u : 0u);
-                    const float4 n0 = __ldg(&sc.nodes[0]), n1 = __ldg(&sc.nodes[1]);
-                    if (slab_test<SLAB>(n0, n1, r, tmax)) { item = sc.root_ref; have = true; }
-                    else finish(ray, out);                           // misses the root box: done at once
-                }
-                continue;
-            }
-            if (idle == full) break;                                 // queue exhausted and every lane finished
-        }
-        if (have) {
-            bool done = false;
-            if (item & TR_REF_LEAF) {
-                uint32_t pi = item & TR_REF_INDEX_MASK;
-                for (;; ++pi) {
-                    const float4 a = __ldg(&sc.prims[3 * pi]);
-                    const uint32_t tag = __float_as_uint(a.w);
-                    if ((tag & ~TR_PRIM_LAST_BIT) == 0u) {
-                        const float4 b = __ldg(&sc.prims[3 * pi + 1]);
-                        const float4 c = __ldg(&sc.prims[3 * pi + 2]);
-                        float t, b0, b1, b2;
-                        if (triangle_test(a, b, c, r, tmax, t, b0, b1, b2)) {
-                            out.prim = pi + 1;
-                            if (ANY) { done = true; break; }
-                            tmax = t; out.t = t; out.b0 = b0; out.b1 = b1;
-                        }
-                    } else if (tag & TR_PRIM_SPHERE_BIT) {
-                        SphereHitInfo sh;
-                        if (sphere_test(sc.spheres[tag & TR_PRIM_INDEX_MASK], r.o, r.d, tmax, sh)) {
-                            out.prim = pi + 1;
-                            if (ANY) { done = true; break; }
-                            tmax = sh.t; out.t = sh.t; out.b0 = 0.0f; out.b1 = 0.0f;
-                        }
-                    }
-                    if (tag & TR_PRIM_LAST_BIT) break;
-                }
-            } else {
-                const float4* np = sc.pairs + 4u * (item & TR_REF_INDEX_MASK);
-                const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-                float t0, t1;
-                const bool s0 = slab_child<SLAB>(q0, q1, r, t0);
-                const bool s1 = slab_child<SLAB>(q2, q3, r, t1);
-                const bool neg = (signs >> (__float_as_uint(q1.w) & 3u)) & 1u;
-                const uint32_t ref0 = __float_as_uint(q1.z), ref1 = __float_as_uint(q3.z);
-                const float near_t = neg ? t1 : t0, far_t = neg ? t0 : t1;
-                const bool near_hit = (neg ? s1 : s0) & (near_t < tmax);
-                const bool far_static = neg ? s0 : s1;
-                const uint32_t near_ref = neg ? ref1 : ref0, far_ref = neg ? ref0 : ref1;
-                if (near_hit) {
-                    item = near_ref;
-                    if (far_static & (cull_far ? !(far_t > tmax + fabsf(tmax) * 1e-3f) : true)) {
-                        if (sp >= TR_STACK_SIZE) { if (error_flag) *error_flag = 1; done = true; }
-                        else { stack[sp++] = tos; tos = make_uint2(far_ref, __float_as_uint(far_t)); }
-                    }
-                    if (!done) continue;
-                } else if (far_static & (far_t < tmax)) { item = far_ref; continue; }
-            }
-            while (!done) {                                          // pop the next pending node t_max still lets in
-                if (sp == 0) { done = true; break; }
-                item = tos.x;
-                const float t_in = __uint_as_float(tos.y);
-                tos = stack[--sp];
-                if (t_in < tmax) break;
-            }
-            if (done) { finish(ray, out); have = false; }
-        }
-    }
-}

@@ -50,29 +50,6 @@ __global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_shadow(DeviceSce
     }
 }
 
-// persistent-warp variants (dynamic ray fetch, traverse.cuh)
-template <int SLAB>
-__global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_extend_p(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
-                                                     const int* __restrict__ count, int cap, float4* __restrict__ hits,
-                                                     int* work_counter, int* error_flag) {
-    const int n = min(*count, cap);
-    trace_persistent<SLAB, false>(sc, ro, rd, n, work_counter, error_flag, [&](int ray, const HitRecord& h) {
-        hits[ray] = make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1);
-    });
-}
-template <int SLAB>
-__global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_shadow_p(DeviceScene sc, const float4* __restrict__ so, const float4* __restrict__ sd,
-                                                     const float4* __restrict__ contrib, const int* __restrict__ count, int cap,
-                                                     float4* __restrict__ accum, int* work_counter, int* error_flag) {
-    const int n = min(*count, cap);
-    trace_persistent<SLAB, true>(sc, so, sd, n, work_counter, error_flag, [&](int ray, const HitRecord& h) {
-        if (h.prim == 0u) {
-            const float4 c = contrib[ray];
-            atomicAdd(&accum[__float_as_int(sd[ray].w)], make_float4(c.x, c.y, c.z, 0.0f));
-        }
-    });
-}
-
 // exact third barycentric of the winning triangle: e2 * inv_det of the same edge functions (pure function of ray + triangle)
 __device__ __forceinline__ float third_barycentric(const DeviceScene& sc, uint32_t prim, float3 o, float3 d) {
     const float4 A = __ldg(&sc.prims[3 * prim]);
@@ -104,36 +81,11 @@ static void launch_shadow_plain(trace_ctx* c, int grid, Args... args) {
 }
 
 
-static int* next_work_counter(trace_ctx* c) {
-    // int counter slots 64..127 are zeroed at the start of every batch / pass; one per traversal launch
-    int* p = ctx_icounters(c) + 64 + (c->work_slot % 64);
-    c->work_slot++;
-    return p;
-}
 static void launch_extend(trace_ctx* c, int grid, DeviceScene sc, const float4* ro, const float4* rd, const int* count, int cap,
                           float4* hits, unsigned long long* counters, int* err) {
-    // dynamic ray fetch (pair walk): "persist" 1 = bounce levels >= 2 only (incoherent rays, long tails), 2 = every level
-    if ((c->persist == 2 || (c->persist == 1 && c->cur_level >= 2)) && !c->count_nodes && c->slab != 1) {
-        c->kev_begin(0);
-        int* wc = next_work_counter(c);
-        if (c->slab == 0) k_wh_extend_p<0><<<occupancy_grid(c, k_wh_extend_p<0>, 128), 128, 0, c->cur_stream>>>(sc, ro, rd, count, cap, hits, wc, err);
-        else k_wh_extend_p<2><<<occupancy_grid(c, k_wh_extend_p<2>, 128), 128, 0, c->cur_stream>>>(sc, ro, rd, count, cap, hits, wc, err);
-        c->stats.kernel_launches++;
-        c->kev_end();
-        return;
-    }
     launch_extend_plain(c, grid, sc, ro, rd, count, cap, hits, counters, err);
 }
 static void launch_shadow(trace_ctx* c, int grid, DeviceScene sc, const float4* so, const float4* sd, const float4* contrib,
                           const int* count, int cap, float4* accum, unsigned long long* counters, int* err) {
-    if (c->persist && !c->count_nodes && c->slab != 1) {
-        c->kev_begin(1);
-        int* wc = next_work_counter(c);
-        if (c->slab == 0) k_wh_shadow_p<0><<<occupancy_grid(c, k_wh_shadow_p<0>, 128), 128, 0, c->cur_stream>>>(sc, so, sd, contrib, count, cap, accum, wc, err);
-        else k_wh_shadow_p<2><<<occupancy_grid(c, k_wh_shadow_p<2>, 128), 128, 0, c->cur_stream>>>(sc, so, sd, contrib, count, cap, accum, wc, err);
-        c->stats.kernel_launches++;
-        c->kev_end();
-        return;
-    }
     launch_shadow_plain(c, grid, sc, so, sd, contrib, count, cap, accum, counters, err);
 }

@@ -40,6 +40,7 @@ struct WhittedLaunch {
     int* counters;             // [level] rays in queue at that level (1-based), [32] shadow rays of the whole batch
     int cap_rays, cap_shadow;
     float4* film_rgbw;         // per film pixel: sum(L*w) rgb, sum(w)
+    unsigned long long* stats; // u64 statistics block of the context
 };
 
 // slot (batch-local, 32-bit) -> pixel, sample, tile.  Batches start on tile boundaries, so no 64-bit arithmetic; with a
@@ -106,20 +107,29 @@ __global__ void __launch_bounds__(256) k_wh_generate(WhittedLaunch L) {
 
 // fused path: generate the camera ray of slot i and trace it right away - hit record i belongs to slot i, there is no
 // primary-ray queue (saves writing and re-reading 48 bytes per sample and one launch per batch)
-template <int SLAB, int WAIT>
-__global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_primary(WhittedLaunch L, int* error_flag) {
-    const DeviceCamera cam = L.frame->cam;
+// the camera sample of slot i as a call (not inlined): its ~40 live values stay out of the traversal loop's registers
+static __device__ __noinline__ bool primary_ray(const WhittedLaunch& L, int i, float3& o, float3& d) {
+    int px, py, s, tile;
+    uint32_t pix = 0;
+    float fx, fy;
     const uint64_t seed = L.frame->seed;
+    if (!slot_film_position(L, seed, i, px, py, s, tile, pix, fx, fy)) return false;
+    slot_camera_ray(L.frame->cam, seed, pix, s, fx, fy, o, d);
+    return true;
+}
+
+template <int SLAB, int WAIT>
+__global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_primary(const __grid_constant__ WhittedLaunch L, int* error_flag) {
     const int lane = threadIdx.x & 31;
     int n_active = 0;
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < L.n_slots; base += gridDim.x * blockDim.x) {
         const int i = base + lane;
-        int px, py, s, tile;
-        uint32_t pix = 0;
-        float fx, fy;
-        const bool valid = i < L.n_slots && slot_film_position(L, seed, i, px, py, s, tile, pix, fx, fy);
         float3 o = f3s(0.0f), d = f3s(1.0f);
-        if (valid) slot_camera_ray(cam, seed, pix, s, fx, fy, o, d);
+        const bool valid = i < L.n_slots && primary_ray(L, i, o, d);
+        // the ray generation above diverges (sample bounds, w == 1 shortcut of the projective divide, lens) and the
+        // compiler does not reconverge the warp before the traversal loop by itself: ncu showed 7 of 32 lanes per
+        // instruction and 3x the run time without this barrier
+        __syncwarp();
         HitRecord h;
         traverse_any<SLAB, false, false, WAIT>(L.sc, valid, o, d, TR_INF, h, nullptr, error_flag);
         if (i < L.n_slots) {
@@ -135,10 +145,13 @@ __global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
     const int cur = (level - 1) & 1, nxt = level & 1;
     const bool rederive = L.fused && level == 1;
     const int n = rederive ? L.n_slots : min(L.counters[level], L.cap_rays);
+    if (level == 1 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&L.stats[ST_PRIMARY_RAYS], (unsigned long long)L.counters[1]);
+    unsigned n_hit = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 h = L.hits[i];
         const uint32_t prim1 = __float_as_uint(h.y);
         if (prim1 == 0u) continue;                          // miss: le(light, ray) == 0 (lights/light.jl:41)
+        n_hit++;
         float4 o4, d4;
         float3 w;
         if (rederive) {
@@ -193,6 +206,11 @@ __global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
                 } else L.counters[IC_OVERFLOW] = 1;
             }
         }
+    }
+    if (level == 1) {                                        // primary hit fraction (reported by bench.py)
+        __syncwarp();
+        n_hit = __reduce_add_sync(0xffffffffu, n_hit);
+        if ((threadIdx.x & 31) == 0 && n_hit) atomicAdd(&L.stats[ST_PRIMARY_HITS], (unsigned long long)n_hit);
     }
 }
 
@@ -341,7 +359,7 @@ static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long 
     L.n_slots = (int)count;
     L.tile_begin = (int)(begin / per_tile);                    // batches start on tile boundaries
     // fused primary stage unless an instrumented pass needs the plain kernels (node counting)
-    L.fused = (c->fuse_primary && !c->count_nodes && c->slab != 1 && !(c->persist == 2)) ? 1 : 0;
+    L.fused = (c->fuse_primary && !c->count_nodes && c->slab != 1) ? 1 : 0;
     int* ic = ctx_icounters(c);
     unsigned long long* st = ctx_stats64(c);
     TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), c->cur_stream));
@@ -355,7 +373,7 @@ static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long 
             k_wh_primary<decltype(S)::value, decltype(W)::value><<<g_trav, 128, 0, c->cur_stream>>>(L, d_err);
         });
         c->kev_end();
-    } else k_wh_generate<<<g_stream, 256, 0, c->cur_stream>>>(L);
+    } else { c->kev_begin(TRACE_K_GENERATE); k_wh_generate<<<g_stream, 256, 0, c->cur_stream>>>(L); c->kev_end(); }
     c->stats.kernel_launches++;
     for (int level = 1; level <= L.max_depth; ++level) {
         const int cur = (level - 1) & 1;
@@ -363,14 +381,18 @@ static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long 
         if (!(L.fused && level == 1))
             launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap_rays,
                           L.hits, st + ST_NODES, d_err);
+        c->kev_begin(TRACE_K_SHADE);
         k_wh_shade<<<occupancy_grid(c, k_wh_shade, 128), 128, 0, c->cur_stream>>>(L, level);
+        c->kev_end();
         c->stats.kernel_launches++;
     }
     // one any-hit launch over the shadow rays of ALL bounce levels of the batch (they only feed the accumulators): a
     // single wide launch instead of max_depth launches that each wait for their slowest ray
     launch_shadow(c, g_trav, L.sc, (const float4*)L.so, (const float4*)L.sd, (const float4*)L.sc_contrib,
                   (const int*)(ic + 32), L.cap_shadow, L.accum, st + ST_NODES, d_err);
+    c->kev_begin(TRACE_K_SPLAT);
     k_wh_splat<<<g_stream, 256, 0, c->cur_stream>>>(L);
+    c->kev_end();
     k_wh_batch_stats<<<1, 32, 0, c->cur_stream>>>(ic, st, L.max_depth, L.cap_rays, L.cap_shadow, batch_flag);
     c->stats.kernel_launches += 2;
     TR_CUDA(c, cudaGetLastError());
@@ -479,6 +501,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     const size_t npix_padded = (npix + (size_t)c->world - 1) / (size_t)c->world * (size_t)c->world;     // equal chunks for the reduce-scatter
     TR_CUDA(c, c->b_queue[12].ensure(npix_padded * sizeof(float4)));
     L.film_rgbw = c->b_queue[12].as<float4>();
+    L.stats = ctx_stats64(c);
     std::vector<WhittedLaunch> lane((size_t)K, L);
     for (int l = 0; l < K; ++l) {
         WhittedLaunch& W = lane[l];

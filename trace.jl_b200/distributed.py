@@ -1,5 +1,7 @@
-"""Multi-GPU drivers: one process per GPU, scene replicated, torch.distributed (NCCL over NVLink) for the two
-exchange steps the path has:
+"""Multi-GPU drivers: one process per GPU, scene replicated.  The two exchange steps the path has run
+INSIDE libtrace_cuda.so on its own NCCL communicator (include/trace_cuda.h: trace_comm_*); this module only hands the
+communicator id from rank 0 to the other ranks (through any torch.distributed backend, or any other channel) and
+keeps the pure-Python partition helpers that the CPU tests exercise with gloo:
 
   * Whitted: 16x16 sample tiles are dealt round-robin to the ranks (tile k -> rank k % world, the reference's
     Threads.@threads loop over tiles, src/integrators/sampler.jl:24); every rank splats into a private full-resolution
@@ -66,98 +68,66 @@ class _DevicePtr:
         self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
-def shares_torch_stream(ctx):
-    """True when the context enqueues on torch's current stream, so torch / NCCL work orders against it by itself."""
+def broadcast_id(make_id, rank, group=None):
+    """Rank 0 creates the communicator id (bytes), every rank returns it.  Any torch.distributed backend will do (it
+    is 128 bytes on the host); tested with gloo on CPU."""
     import torch
-    return bool(ctx.stream_handle) and ctx.stream_handle == torch.cuda.current_stream().cuda_stream
-
-
-class _Fence:
-    """Orders a block of torch work (collectives) against the context's stream.  Nothing to do when both use the same
-    stream; otherwise the context's stream is drained before and torch's current stream after."""
-
-    def __init__(self, ctx):
-        self.ctx, self.shared = ctx, shares_torch_stream(ctx)
-
-    def __enter__(self):
-        if not self.shared:
-            self.ctx.synchronize()
-        return self
-
-    def __exit__(self, *exc):
-        if not self.shared:
-            import torch
-            torch.cuda.current_stream().synchronize()
-        return False
+    import torch.distributed as dist
+    buf = torch.zeros(_lib.COMM_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        buf = torch.frombuffer(bytearray(make_id()), dtype=torch.uint8).clone()
+    if dist.get_backend(group) == "nccl":
+        dev = buf.cuda()
+        dist.broadcast(dev, src=0, group=group)
+        buf = dev.cpu()
+    else:
+        dist.broadcast(buf, src=0, group=group)
+    return bytes(buf.numpy().tobytes())
 
 
 def allreduce_sum(tensor, group=None):
-    """all_reduce(sum) when a process group exists; identity otherwise.  Backend-agnostic (nccl on GPUs, gloo in tests)."""
+    """all_reduce(sum) when a process group exists; identity otherwise (host-side bookkeeping of the drivers, e.g. ray
+    counters; backend-agnostic: nccl on GPUs, gloo in the CPU tests)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
     return tensor
 
 
-def render_whitted_sharded(ctx, scene, camera, spp, max_depth, seed, film_tensor, rank=0, world=1, group=None, reduce=True):
-    """Render this rank's tiles into `film_tensor` (torch float32 [H, W, 4] on the context's GPU), then reduce to rank 0."""
-    import torch.distributed as dist
+def init_comm(ctx, rank, world, group=None):
+    """Give `ctx` the library's NCCL communicator over the ranks of the torch.distributed group."""
+    from .render import comm_unique_id
+    if world <= 1:
+        return
+    ctx.comm_init(broadcast_id(comm_unique_id, rank, group), rank, world)
+
+
+def render_whitted_sharded(ctx, scene, camera, spp, max_depth, seed, film_tensor, rank=0, world=1, reduce=False):
+    """One Whitted render into `film_tensor` (torch float32 [H, W, 4] on the context's GPU).  With a communicator
+    (init_comm) this is the whole multi-GPU render: the library renders the rank's tiles and sums the films (option
+    "film_mode": everything on rank 0, or one band per rank).  Without one, (rank, world) only select the tiles - used to
+    play one rank of N on a single GPU."""
     flat = ctx.upload(scene)
     if flat.has_unshaded:
         raise ValueError("every primitive needs a material")
-    ctx.set_option("world", world)
-    ctx.set_option("rank", rank)
+    if not ctx.comm_info()["nccl_version"]:
+        ctx.set_option("world", world)
+        ctx.set_option("rank", rank)
     cam, fd = camera.pod(), camera.film.desc()
     ctx.check(ctx.lib.trace_render_whitted_device(ctx.h, C.byref(cam), C.byref(fd), int(spp), int(max_depth),
                                                   C.c_uint64(seed), C.c_void_p(film_tensor.data_ptr())))
-    if reduce and world > 1:
-        with _Fence(ctx):
-            dist.reduce(film_tensor, dst=0, op=dist.ReduceOp.SUM, group=group)
     return film_tensor
 
 
-class ShardedWhittedRenderer:
-    """Whitted render over `world` ranks with a HOST film (the reference's accumulate-into-film semantics, film.jl:182-193):
-    every rank renders its tiles into a zeroed device film, one reduce(sum) to rank 0, and rank 0 adds the caller's
-    film - uploaded on a copy stream WHILE the render runs - and copies the sum back.  `host_film` (rank 0; pinned for
-    the copies to be asynchronous) is float32 [H, W, 4]; other ranks pass None."""
-
-    def __init__(self, ctx, scene, camera, rank=0, world=1, group=None):
-        import torch
-        self.ctx, self.scene, self.camera, self.rank, self.world, self.group = ctx, scene, camera, rank, world, group
-        h, w = camera.film.pixels.shape[:2]
-        dev = f"cuda:{torch.cuda.current_device()}"
-        self.film_dev = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
-        self.staging = torch.zeros((h, w, 4), dtype=torch.float32, device=dev) if rank == 0 else None
-        self.copy_stream = torch.cuda.Stream() if rank == 0 else None
-        self.uploaded = torch.cuda.Event() if rank == 0 else None
-
-    def render(self, host_film, spp, max_depth, seed):
-        import torch
-        cur = torch.cuda.current_stream()
-        if self.rank == 0:
-            self.copy_stream.wait_stream(cur)                    # (the previous render's add_ has read `staging`)
-            with torch.cuda.stream(self.copy_stream):
-                self.staging.copy_(host_film, non_blocking=True)
-                self.uploaded.record()
-        self.film_dev.zero_()
-        render_whitted_sharded(self.ctx, self.scene, self.camera, spp, max_depth, seed, self.film_dev, self.rank, self.world,
-                               self.group, reduce=True)
-        if self.rank == 0:
-            cur.wait_event(self.uploaded)
-            self.film_dev.add_(self.staging)
-            host_film.copy_(self.film_dev, non_blocking=True)
-        cur.synchronize()
-        return host_film
-
-
 class SPPMSession:
-    """Stepwise SPPM (trace_sppm_begin / camera_pass / photon_pass / update / image) with photon sharding."""
+    """SPPM over the ranks of the context's communicator (or on one GPU): trace_sppm_begin, then step() = one iteration
+    (sppm.jl:153-165) enqueued by trace_sppm_iterate - camera paths sharded by image rows, photons by index range, the
+    all-gather of the visible points and the all-reduce of (Phi, M) inside the library.  `emulate=(rank, world)` plays
+    one rank without a communicator through the stepwise API (the caller moves the slices; tests only)."""
 
     def __init__(self, ctx, scene, camera, initial_search_radius, max_depth, photons_per_iteration=-1, seed=0x5EED0001,
-                 rank=0, world=1, group=None):
-        import torch
-        self.ctx, self.camera, self.rank, self.world, self.group = ctx, camera, rank, world, group
+                 emulate=None):
+        self.ctx, self.camera = ctx, camera
         flat = ctx.upload(scene)
         if flat.has_unshaded:
             raise ValueError("every primitive needs a material")
@@ -165,63 +135,35 @@ class SPPMSession:
             photons_per_iteration = int(camera.film.crop_bounds.area())
         self.photons = int(photons_per_iteration)
         cam, fd = camera.pod(), camera.film.desc()
-        ctx.set_option("world", world)
-        ctx.set_option("rank", rank)
+        info = ctx.comm_info()
+        self.rank, self.world = info["rank"], info["world"]
+        if emulate is not None:
+            self.rank, self.world = emulate
+            ctx.set_option("world", self.world)
+            ctx.set_option("rank", self.rank)
+        elif not info["nccl_version"]:
+            ctx.set_option("world", 1)
+            ctx.set_option("rank", 0)
+            self.rank, self.world = 0, 1
         ctx.check(ctx.lib.trace_sppm_begin(ctx.h, C.byref(cam), C.byref(fd), float(initial_search_radius), int(max_depth),
                                            self.photons, C.c_uint64(seed)))
-        self.buffers = None
-        self._vp_recv = None
-        if world > 1:
-            dev = f"cuda:{torch.cuda.current_device()}"
-            self.buffers = []
-            for which in range(7):          # 0 flux, 1 Ld, 2..6 visible-point records (storage order, rank-major slices)
-                n = C.c_int64()
-                ptr = ctx.lib.trace_sppm_buffer_device(ctx.h, which, C.byref(n))
-                self.buffers.append(torch.as_tensor(_DevicePtr(ptr, n.value), device=dev))
         self.iteration = 0
 
-    def _all_gather(self, which):
-        import torch.distributed as dist
-        t = self.buffers[which]
-        n = t.numel() // self.world
-        dist.all_gather_into_tensor(t, t[self.rank * n:(self.rank + 1) * n].clone(), group=self.group)
+    def step(self, n=1):
+        self.ctx.check(self.ctx.lib.trace_sppm_iterate(self.ctx.h, self.iteration + 1, int(n)))
+        self.iteration += int(n)
 
-    def _gather_visible_points(self):
-        """ONE all-gather for the five visible-point arrays: this rank's five slices are packed into one send buffer,
-        gathered as [world][5][slice], and scattered back into the arrays' rank slices (two small copy kernels instead
-        of four more collectives, whose launch latency dominates at these sizes)."""
+    def buffers(self):
+        """The seven per-pixel device buffers (storage order) as torch views: 0 flux, 1 Ld, 2..6 visible points."""
         import torch
-        import torch.distributed as dist
-        arrays = self.buffers[2:7]
-        n = arrays[0].numel() // self.world
-        send = torch.stack([a[self.rank * n:(self.rank + 1) * n] for a in arrays])          # [5][n]
-        if self._vp_recv is None:
-            self._vp_recv = torch.empty((self.world, len(arrays), n), dtype=send.dtype, device=send.device)
-        dist.all_gather_into_tensor(self._vp_recv, send, group=self.group)
-        for k, a in enumerate(arrays):
-            a.view(self.world, n).copy_(self._vp_recv[:, k, :])
-
-    def step(self):
-        """One SPPM iteration (sppm.jl:153-165) over all ranks."""
-        self.iteration += 1
-        ctx = self.ctx
-        b, e = photon_range(self.photons, self.rank, self.world)
-        ctx.check(ctx.lib.trace_sppm_trace_photons(ctx.h, self.iteration, b, e))     # asynchronous: overlaps what follows
-        ctx.check(ctx.lib.trace_sppm_camera_pass(ctx.h, self.iteration))
-        if self.world > 1:
-            with _Fence(ctx):
-                self._gather_visible_points()
-            ctx.check(ctx.lib.trace_sppm_build_grid(ctx.h))
-        ctx.check(ctx.lib.trace_sppm_photon_pass(ctx.h, self.iteration, b, e))
-        if self.world > 1:
-            with _Fence(ctx):
-                allreduce_sum(self.buffers[0], self.group)
-        ctx.check(ctx.lib.trace_sppm_update(ctx.h))
+        out = []
+        for which in range(7):
+            n = C.c_int64()
+            ptr = self.ctx.lib.trace_sppm_buffer_device(self.ctx.h, which, C.byref(n))
+            out.append(torch.as_tensor(_DevicePtr(ptr, n.value), device=f"cuda:{torch.cuda.current_device()}"))
+        return out
 
     def image(self):
-        if self.world > 1:
-            with _Fence(self.ctx):
-                self._all_gather(1)         # Ld is accumulated only by the rank that owns the row
         h, w = self.camera.film.pixels.shape[:2]
         rgb = np.zeros((h, w, 3), dtype=np.float32)
         self.ctx.check(self.ctx.lib.trace_sppm_image(self.ctx.h, max(1, self.iteration), _lib.ptr(rgb)))

@@ -179,6 +179,22 @@ class Context:
     def set_option(self, key, value):
         self.check(self.lib.trace_set_option(self.h, key.encode(), int(value)))
 
+    # multi-GPU: the library's own NCCL communicator (include/trace_cuda.h, trace_comm_*)
+    def comm_init(self, comm_id, rank, world):
+        """Collective: every rank calls it with the SAME id (bytes from `comm_unique_id()` on rank 0)."""
+        if len(comm_id) != _lib.COMM_ID_BYTES:
+            raise ValueError("communicator id must be %d bytes" % _lib.COMM_ID_BYTES)
+        buf = C.create_string_buffer(bytes(comm_id), _lib.COMM_ID_BYTES)
+        self.check(self.lib.trace_comm_init(self.h, buf, int(rank), int(world)))
+
+    def comm_destroy(self):
+        self.check(self.lib.trace_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self.check(self.lib.trace_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
     def upload(self, scene):
         flat = scene.flatten()
         if self._scene is not flat:
@@ -222,6 +238,15 @@ class Context:
         out = np.zeros(n, dtype=np.uint8)
         self.check(self.lib.trace_occluded(self.h, _lib.ptr(o), _lib.ptr(d), _lib.ptr(t), n, _lib.ptr(out)))
         return out.astype(bool)
+
+
+def comm_unique_id():
+    """128-byte id of a new communicator (rank 0 creates it and hands it to the other ranks out of band)."""
+    buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+    rc = _lib.load().trace_comm_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError(f"trace_comm_unique_id failed ({rc}): libnccl.so.2 could not be loaded")
+    return buf.raw
 
 
 _default_ctx = None

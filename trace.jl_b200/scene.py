@@ -288,6 +288,10 @@ def _expand(primitives):
     return items
 
 
+# optional replacement of the native tree build: f(prim_bounds [n,6], max_node_primitives, builder) -> (nodes, order)
+BVH_BUILD_HOOK = None
+
+
 class BVHAccel:
     """BVHAccel(primitives, max_node_primitives = 1), src/accel/bvh.jl:50-80.  The build itself is
     trace_bvh_build in libtrace_cuda.so's host part (the reference's SAH split logic)."""
@@ -295,7 +299,6 @@ class BVHAccel:
     def __init__(self, primitives, max_node_primitives=1, builder="reference"):
         """builder = "reference": the reference's split logic, bit-identical tree (src/accel/bvh.jl:55-206).
         builder = "sah": opt-in conventional binned SAH (trace_bvh_build_sah) - same hits, ties aside; less traversal."""
-        lib = _lib.load()
         if builder not in ("reference", "sah"):
             raise ValueError("builder must be 'reference' or 'sah'")
         self.builder = builder
@@ -322,6 +325,10 @@ class BVHAccel:
             self.order = np.zeros(0, dtype=np.uint32)
             return
         self.prim_bounds = np.ascontiguousarray(np.concatenate(bounds, axis=0), dtype=np.float32)
+        if BVH_BUILD_HOOK is not None:      # (bench.py --impl reference: the checker's builder, no product library in the process)
+            self.nodes, self.order = BVH_BUILD_HOOK(self.prim_bounds, self.max_node_primitives, builder)
+            return
+        lib = _lib.load()
         h = C.c_void_p()
         build = lib.trace_bvh_build if builder == "reference" else lib.trace_bvh_build_sah
         rc = build(_lib.ptr(self.prim_bounds), self.n_primitives, self.max_node_primitives, C.byref(h))
