@@ -5,6 +5,7 @@
 #
 #   using Trace, TraceCUDA
 #   scene |> TraceCUDA.gpu(Trace.SPPMIntegrator(camera, 0.025f0, 5, 100))      # instead of  scene |> integrator
+#   scene |> TraceCUDA.gpu(integrator, TraceCUDA.MultiContext(0:7))            # all eight GPUs of the box (julia -t 8)
 #
 module TraceCUDA
 
@@ -70,15 +71,42 @@ rowmajor(m::Mat4f) = ntuple(k -> m[(k - 1) ÷ 4 + 1, (k - 1) % 4 + 1], 16)
 mutable struct Context
     h::Ptr{Cvoid}
     lock::ReentrantLock
-    function Context(device::Integer = 0)
+    seed::UInt64            # renders draw seed, seed + 1, ...: a fixed seed makes Julia-side renders reproducible
+    function Context(device::Integer = 0; seed::Integer = 0x5EED0001)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:trace_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Cvoid}), out, device, C_NULL)
         rc == 0 || error("trace_create failed ($rc): no CUDA device (there is no CPU fallback)")
-        ctx = new(out[], ReentrantLock())
+        ctx = new(out[], ReentrantLock(), UInt64(seed))
         finalizer(c -> ccall((:trace_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.h), ctx)
     end
 end
 check(ctx, rc) = rc == 0 || error(unsafe_string(ccall((:trace_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h)))
+set_option!(ctx::Context, key::AbstractString, v::Integer) =
+    check(ctx, ccall((:trace_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), ctx.h, key, v))
+next_seed!(ctx::Context) = (s = ctx.seed; ctx.seed += 1; s)
+
+# ---- several GPUs of one box: one Context per device, one Julia task per Context ------------------------------------------
+# The reference parallelises with Threads.@threads over tiles / photons into shared arrays; across GPUs the library runs
+# the two exchange steps itself on NCCL (trace_comm_init).  Here: one process, `Threads.@spawn` per device, all ranks share
+# the id through a captured variable, and - film_mode 1 - every GPU writes ITS band of the one shared host film.
+struct MultiContext
+    ctxs::Vector{Context}
+end
+function MultiContext(devices::AbstractVector{<:Integer}; seed::Integer = 0x5EED0001)
+    ctxs = [Context(d; seed = seed) for d in devices]          # the same seed on every rank: ranks must agree on it
+    id = zeros(UInt8, 128)                                      # TRACE_COMM_ID_BYTES
+    ccall((:trace_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error("libnccl.so.2 could not be loaded")
+    world = length(ctxs)
+    @sync for (r, c) in enumerate(ctxs)                         # trace_comm_init is collective: all ranks concurrently
+        Threads.@spawn check(c, ccall((:trace_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), c.h, id, r - 1, world))
+    end
+    foreach(c -> set_option!(c, "film_mode", 1), ctxs)
+    MultiContext(ctxs)
+end
+# run f(ctx) on every rank concurrently (every rank must make the same sequence of render calls)
+on_all(f, m::MultiContext) = @sync for c in m.ctxs
+    Threads.@spawn f(c)
+end
 
 # ---- flattening Trace.Scene -> SceneDesc (what trace.jl_b200/scene.py:FlatScene does) -------------------------------
 # BVHAccel.nodes are already the reference's LinearBVH array (1-based); convert to 0-based trace_bvh_node.
@@ -98,9 +126,16 @@ const MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_PLASTIC = UInt32(0), UInt32(1), UInt
 const LIGHT_POINT, LIGHT_SPOT, LIGHT_DIRECTIONAL = UInt32(0), UInt32(1), UInt32(2)
 const NO_MATERIAL = 0xFFFFFFFF
 
-# Only constant textures are supported on the device (the three docs/code scenes use nothing else).
+# Textures: the leaves the reference can build without a 2D mapping are constant, so Scale / Mix trees do not vary over the
+# surface; they fold here (Float32, the operation order of src/textures/basic.jl:17-36) into the constant the device
+# material carries.  BilerpTexture needs a mapping and is not supported.
 texval(t::Trace.ConstantTexture) = t.value
-texval(t) = error("TraceCUDA: only ConstantTexture is supported on the GPU path, got $(typeof(t))")
+texval(t::Trace.ScaleTexture) = texval(t.texture_1) * texval(t.texture_2)
+function texval(t::Trace.MixTexture)
+    m::Float32 = texval(t.mix)
+    (1 - m) * texval(t.texture_1) + m * texval(t.texture_2)
+end
+texval(t) = error("TraceCUDA: only Constant / Scale / Mix textures are supported on the GPU path, got $(typeof(t))")
 rgb3(s::Trace.RGBSpectrum) = (s.c[1], s.c[2], s.c[3])
 const ZERO3 = (0f0, 0f0, 0f0)
 
@@ -221,11 +256,11 @@ function upload!(ctx::Context, scene::Trace.Scene)
 end
 
 # ---- the two functors ------------------------------------------------------------------------------------------------
-struct GPU{I<:Trace.Integrator}
+struct GPU{I<:Trace.Integrator,C}
     integrator::I
-    ctx::Context
+    ctx::C                 # Context (one GPU) or MultiContext (several GPUs of the box)
 end
-gpu(i::Trace.Integrator, ctx::Context = Context()) = GPU(i, ctx)
+gpu(i::Trace.Integrator, ctx = Context()) = GPU(i, ctx)
 
 camera_pod(c::Trace.PerspectiveCamera) = CameraP(
     rowmajor(c.core.raster_to_camera.m), rowmajor(c.core.core.camera_to_world.m),
@@ -237,8 +272,16 @@ function film_pod(f::Trace.Film)
 end
 
 # (i::SamplerIntegrator)(scene)  — src/integrators/sampler.jl:12-56
+function render_whitted!(ctx::Context, i, scene, film, buf)
+    lock(ctx.lock) do
+        upload!(ctx, scene)
+        GC.@preserve buf check(ctx, ccall((:trace_render_whitted, LIB), Cint,
+            (Ptr{Cvoid}, Ref{CameraP}, Ref{FilmP}, Cint, Cint, UInt64, Ptr{Float32}),
+            ctx.h, camera_pod(i.camera), film_pod(film), i.sampler.samples_per_pixel, i.max_depth, next_seed!(ctx), buf))
+    end
+end
 function (g::GPU{Trace.WhittedIntegrator})(scene::Trace.Scene)
-    i, ctx = g.integrator, g.ctx
+    i = g.integrator
     film = Trace.get_film(i.camera)
     H, W = size(film.pixels)
     buf = zeros(Float32, 4, W, H)                       # row-major [y][x][4] on the C side
@@ -246,11 +289,12 @@ function (g::GPU{Trace.WhittedIntegrator})(scene::Trace.Scene)
         p = film.pixels[y, x]
         buf[1:3, x, y] .= p.xyz; buf[4, x, y] = p.filter_weight_sum
     end
-    lock(ctx.lock) do
-        upload!(ctx, scene)
-        GC.@preserve buf check(ctx, ccall((:trace_render_whitted, LIB), Cint,
-            (Ptr{Cvoid}, Ref{CameraP}, Ref{FilmP}, Cint, Cint, UInt64, Ptr{Float32}),
-            ctx.h, camera_pod(i.camera), film_pod(film), i.sampler.samples_per_pixel, i.max_depth, rand(UInt64), buf))
+    if g.ctx isa MultiContext
+        # every rank renders its tiles; the library sums the films and every GPU uploads / merges / downloads its own band
+        # of `buf` (film_mode 1), so the bands travel over as many PCIe links as there are GPUs
+        on_all(c -> render_whitted!(c, i, scene, film, buf), g.ctx)
+    else
+        render_whitted!(g.ctx, i, scene, film, buf)
     end
     for y in 1:H, x in 1:W
         film.pixels[y, x].xyz = Point3f(buf[1:3, x, y]); film.pixels[y, x].filter_weight_sum = buf[4, x, y]
@@ -259,7 +303,27 @@ function (g::GPU{Trace.WhittedIntegrator})(scene::Trace.Scene)
 end
 
 # (i::SPPMIntegrator)(scene)  — src/integrators/sppm.jl:132-173
-function (g::GPU{Trace.SPPMIntegrator})(scene::Trace.Scene)
+function (g::GPU{Trace.SPPMIntegrator,MultiContext})(scene::Trace.Scene)
+    # camera paths by image rows, photons by index range; the all-gather of the visible points and the all-reduce of
+    # (Phi, M) run inside trace_render_sppm.  Every rank returns the whole image; rank 0's drives the film / PNG writes.
+    i = g.integrator
+    film = Trace.get_film(i.camera)
+    H, W = size(film.pixels)
+    images = [zeros(Float32, 3, W, H) for _ in g.ctx.ctxs]
+    @sync for (r, c) in enumerate(g.ctx.ctxs)
+        Threads.@spawn lock(c.lock) do
+            upload!(c, scene)
+            GC.@preserve images check(c, ccall((:trace_render_sppm, LIB), Cint,
+                (Ptr{Cvoid}, Ref{CameraP}, Ref{FilmP}, Cfloat, Cint, Cint, Int64, Cint, UInt64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float32}),
+                c.h, camera_pod(i.camera), film_pod(film), i.initial_search_radius, i.max_depth, i.n_iterations,
+                i.photons_per_iteration, 0, next_seed!(c), C_NULL, C_NULL, images[r]))
+        end
+    end
+    img = images[1]
+    Trace.set_image!(film, [Trace.RGBSpectrum(img[1, x, y], img[2, x, y], img[3, x, y]) for y in 1:H, x in 1:W])
+    Trace.save(film)
+end
+function (g::GPU{Trace.SPPMIntegrator,Context})(scene::Trace.Scene)
     i, ctx = g.integrator, g.ctx
     film = Trace.get_film(i.camera)
     H, W = size(film.pixels)
@@ -276,7 +340,7 @@ function (g::GPU{Trace.SPPMIntegrator})(scene::Trace.Scene)
         GC.@preserve rgb cb check(ctx, ccall((:trace_render_sppm, LIB), Cint,
             (Ptr{Cvoid}, Ref{CameraP}, Ref{FilmP}, Cfloat, Cint, Cint, Int64, Cint, UInt64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float32}),
             ctx.h, camera_pod(i.camera), film_pod(film), i.initial_search_radius, i.max_depth, i.n_iterations,
-            i.photons_per_iteration, i.write_frequency, rand(UInt64), cb, C_NULL, rgb))
+            i.photons_per_iteration, i.write_frequency, next_seed!(ctx), cb, C_NULL, rgb))
     end
 end
 

@@ -183,3 +183,29 @@ def test_gloo_world2_tile_shard_and_allreduce(tmp_path):
                         "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_scale_and_mix_textures_fold_like_the_reference():
+    """ScaleTexture / MixTexture (src/textures/basic.jl:12-37) over constant leaves: t1 * t2 and (1 - t) * t1 + t * t2 in
+    Float32, evaluated when the material is flattened; the device receives the constant."""
+    import trace_jl_b200 as T
+    from trace_jl_b200.scene import _tex_rgb, _tex_f
+    f32 = np.float32
+    a, b = T.ConstantTexture(T.RGBSpectrum(0.8, 0.5, 0.25)), T.ConstantTexture(T.RGBSpectrum(0.5, 0.25, 0.1))
+    t = T.ConstantTexture(0.3)
+    got = _tex_rgb(T.ScaleTexture(a, b))
+    assert got.dtype == np.float32 and np.array_equal(got, (a.value.c * b.value.c).astype(f32))
+    mix = _tex_rgb(T.MixTexture(a, b, t))
+    want = ((f32(1) - f32(0.3)) * a.value.c + f32(0.3) * b.value.c).astype(f32)
+    assert np.array_equal(mix, want)
+    # nested, and scalar textures (roughness / sigma / index)
+    nested = _tex_rgb(T.ScaleTexture(T.MixTexture(a, b, t), T.ConstantTexture(T.RGBSpectrum(2.0))))
+    assert np.array_equal(nested, (want * f32(2)).astype(f32))
+    assert _tex_f(T.MixTexture(T.ConstantTexture(0.1), T.ConstantTexture(0.5), T.ConstantTexture(0.25))) == f32(f32(0.75) * f32(0.1) + f32(0.25) * f32(0.5))
+    with pytest.raises(TypeError):
+        _tex_f(a)
+    with pytest.raises(TypeError):
+        _tex_rgb(T.MixTexture(a, b, a))
+    # the material POD carries the folded value
+    m = T.MatteMaterial(T.ScaleTexture(a, b), T.ConstantTexture(0.0))
+    assert np.array_equal(np.asarray(m.pod()[1]), got)

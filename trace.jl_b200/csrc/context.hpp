@@ -11,6 +11,24 @@
 
 #include "device_common.cuh"
 
+// NVTX ranges around the wavefront stages: header-only NVTX3, a no-op unless a profiler is attached
+#if defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define TR_HAVE_NVTX 1
+#endif
+#endif
+struct TrRange {
+#ifdef TR_HAVE_NVTX
+    explicit TrRange(const char* name) { nvtxRangePushA(name); }
+    ~TrRange() { nvtxRangePop(); }
+#else
+    explicit TrRange(const char*) {}
+#endif
+    TrRange(const TrRange&) = delete;
+    TrRange& operator=(const TrRange&) = delete;
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;

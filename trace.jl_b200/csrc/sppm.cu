@@ -681,6 +681,7 @@ struct LaneScope {
 };
 
 static int sppm_camera_lane(trace_ctx* c, SppmState* s, int l, int iteration) {
+    TrRange nvtx("sppm.camera pass");
     SppmLaunch& W = s->cam_lane[l];
     W.iteration = iteration;
     cudaStream_t st = c->cur_stream;
@@ -749,6 +750,7 @@ extern "C" int trace_sppm_build_grid(trace_ctx* c) {
     return check_flags(c, "trace_sppm_build_grid");
 }
 static int sppm_build_grid_async(trace_ctx* c) {
+    TrRange nvtx("sppm.grid build");
     if (!c) return 1;
     cudaSetDevice(c->device);
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_build_grid: call trace_sppm_begin first");
@@ -777,6 +779,7 @@ static int sppm_build_grid_async(trace_ctx* c) {
 // Photon tracing of [begin, end) on the photon lanes: generate -> (extend -> shade) x depth.  The shade kernel leaves
 // deposit REQUESTS (hit point, direction, weight) in the lane's request queue; nothing here reads the grid.
 static int sppm_trace_lane(trace_ctx* c, SppmState* s, int j, int iteration, int64_t b, int n) {
+    TrRange nvtx("sppm.photon tracing");
     SppmLaunch& W = s->ph_lane[j];
     W.iteration = iteration;
     W.photon_begin = b;
@@ -805,6 +808,7 @@ static int sppm_trace_lane(trace_ctx* c, SppmState* s, int j, int iteration, int
 }
 
 static int sppm_deposit_lane(trace_ctx* c, SppmState* s, int j) {
+    TrRange nvtx("sppm.photon deposit");
     SppmLaunch& W = s->ph_lane[j];
     cudaStream_t st = c->cur_stream;
     // deposit requests of all bounce levels in one launch (deposits do not feed back into the photon paths)
@@ -936,6 +940,7 @@ extern "C" int trace_sppm_end(trace_ctx* c) {
 // the two exchange steps of SURVEY.md 8e run here: all-gather of the visible points (camera paths are sharded by image
 // rows) and all-reduce(sum) of (Phi, M) (photons are sharded by index range).
 static int sppm_iteration_async(trace_ctx* c, int it) {
+    TrRange nvtx("sppm.iteration");
     SppmState* s = c->sppm;
     SppmLaunch& L = s->L;
     const bool multi = c->comm != nullptr && c->world > 1;

@@ -354,6 +354,7 @@ __global__ void k_wh_batch_stats(int* counters, unsigned long long* stats, int m
 // sync cost ~0.9 ms of GPU idle time per batch on B200: 17 launches to enqueue behind an empty stream).
 static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long count, int depth_guard, int* batch_flag = nullptr) {
     if (count <= 0) return 0;
+    TrRange nvtx_batch("whitted.batch: primary -> (extend -> shade) x depth -> shadow -> splat");
     const long long per_tile = 256ll * L.spp;
     L.slot_begin = begin;
     L.n_slots = (int)count;
@@ -428,6 +429,7 @@ void whitted_film_range(const trace_ctx* c, long long npix, long long* p0, long 
 
 int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_film_desc* film, int spp, int max_depth,
                           uint64_t seed, float* film_dev) {
+    TrRange nvtx_render("trace_render_whitted");
     if (c->rank < 0 || c->rank >= c->world) return c->fail("rank %d outside world %d", c->rank, c->world);
     if (max_depth < 1 || max_depth > TR_MAX_DEPTH) return c->fail("max_depth must be in [1, %d]", TR_MAX_DEPTH);
     WhittedLaunch L;
@@ -614,6 +616,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     }
     if (multi) {
         // the ONE exchange of a Whitted render: sum of the ranks' private films, on the render's stream
+        TrRange nvtx_sum("whitted.film sum (NCCL)");
         float* rgbw = reinterpret_cast<float*>(L.film_rgbw);
         const float4* merged = L.film_rgbw;
         if (c->film_mode == 0) { if (comm_reduce_sum(c, rgbw, rgbw, npix * 4, 0)) return 1; }

@@ -37,15 +37,51 @@ class ConstantTexture:
         self.value = value
 
 
+class ScaleTexture:
+    """src/textures/basic.jl:12-19: texture_1(si) * texture_2(si)."""
+    __slots__ = ("texture_1", "texture_2")
+
+    def __init__(self, texture_1, texture_2):
+        self.texture_1, self.texture_2 = texture_1, texture_2
+
+
+class MixTexture:
+    """src/textures/basic.jl:21-37: (1 - t) * texture_1(si) + t * texture_2(si) with t = mix(si)::Float32."""
+    __slots__ = ("texture_1", "texture_2", "mix")
+
+    def __init__(self, texture_1, texture_2, mix):
+        self.texture_1, self.texture_2, self.mix = texture_1, texture_2, mix
+
+
+def _tex_value(t):
+    """Value of a texture tree as the reference evaluates it at a hit.  The leaves the reference can build without a
+    2D mapping are ConstantTextures, so Scale / Mix trees do not vary over the surface: they fold, in Float32 and in
+    the reference's operation order, into the constant the device material carries (Bilerp / mappings: out of scope)."""
+    if isinstance(t, ConstantTexture):
+        v = t.value
+        return v.c.astype(np.float32) if isinstance(v, RGBSpectrum) else f32(v)
+    if isinstance(t, ScaleTexture):
+        return (_tex_value(t.texture_1) * _tex_value(t.texture_2)).astype(np.float32)
+    if isinstance(t, MixTexture):
+        m = _tex_value(t.mix)
+        if np.ndim(m) != 0:
+            raise TypeError("MixTexture: `mix` must be a Float32 texture (textures/basic.jl:34)")
+        m = f32(m)
+        return ((f32(1) - m) * _tex_value(t.texture_1) + m * _tex_value(t.texture_2)).astype(np.float32)
+    if isinstance(t, RGBSpectrum):
+        return t.c.astype(np.float32)
+    return f32(t)
+
+
 def _tex_rgb(t):
-    v = t.value if isinstance(t, ConstantTexture) else t
-    if isinstance(v, RGBSpectrum):
-        return v.c
-    return np.full(3, v, dtype=np.float32)
+    v = _tex_value(t)
+    return v if np.ndim(v) else np.full(3, v, dtype=np.float32)
 
 
 def _tex_f(t):
-    v = t.value if isinstance(t, ConstantTexture) else t
+    v = _tex_value(t)
+    if np.ndim(v):
+        raise TypeError("a Float32 texture is required here, got a spectrum")
     return f32(v)
 
 
