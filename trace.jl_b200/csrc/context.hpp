@@ -72,6 +72,7 @@ struct trace_ctx {
     int count_nodes = 0;
     int cap_percent = 200;        // ray-queue capacity per bounce level, in % of the batch size
     int persist = 0;              // dynamic ray fetch in the traversal kernels: 0 off, 1 bounce levels >= 2 and shadow rays, 2 all
+    int sppm_path = 0;            // SPPM: bounce levels the fused path kernel carries before handing over to the wavefront queues (0: none)
     int fuse_primary = 1;         // Whitted: generate + trace the camera rays in one kernel (no primary-ray queue)
     int cur_level = 0;            // bounce level of the extend launch being enqueued (set by the integrators)
     int work_slot = 0;

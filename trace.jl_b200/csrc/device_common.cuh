@@ -107,6 +107,18 @@ struct DeviceFilm {
     int width, height;
 };
 
+// ------------------------------------------------------------------ queue traffic: streamed once, evict-first
+// Ray / hit / shadow queues are written by one kernel and read once by the next; the BVH (64 MB of pair nodes + 48 MB
+// of primitives on tess-1M) is what should stay in the 126 MB L2.  ld.global.cs / st.global.cs mark the queue lines
+// evict-first.
+#ifdef TR_NO_STREAM_HINTS
+__device__ __forceinline__ float4 q_load(const float4* p) { return *p; }
+__device__ __forceinline__ void q_store(float4* p, float4 v) { *p = v; }
+#else
+__device__ __forceinline__ float4 q_load(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void q_store(float4* p, float4 v) { __stcs(p, v); }
+#endif
+
 // ------------------------------------------------------------------ queue push with warp-aggregated atomics
 __device__ __forceinline__ int queue_claim(int* counter) {
     cg::coalesced_group g = cg::coalesced_threads();

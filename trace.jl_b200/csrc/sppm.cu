@@ -75,18 +75,25 @@ __device__ __forceinline__ int raster_to_storage(const SppmLaunch& L, int x, int
 // ---------------------------------------------------------------- camera pass
 // One camera path per pixel of THIS rank's rows (sppm.jl:184-196). The RNG is keyed by the raster pixel index, so the
 // visible points do not depend on the number of ranks.
+// the camera ray of storage slot `st` (false: padding slot); the RNG is keyed by the raster pixel
+__device__ __forceinline__ bool cam_generate_ray(const SppmLaunch& L, int st, int& pix, float3& o, float3& d) {
+    int x, y;
+    if (!storage_to_raster(L, st, x, y)) return false;
+    pix = y * L.W + x;      // raster index: RNG key
+    const int px = L.film.crop_x0 + x, py = L.film.crop_y0 + y;
+    const uint32_t it = (uint32_t)L.iteration;
+    const float u0 = rng_uniform(L.seed, (uint32_t)pix, it, 0), u1 = rng_uniform(L.seed, (uint32_t)pix, it, 1);
+    float l0 = 0.0f, l1 = 0.0f;
+    if (L.cam.lens_radius > 0.0f) { l0 = rng_uniform(L.seed, (uint32_t)pix, it, 2); l1 = rng_uniform(L.seed, (uint32_t)pix, it, 3); }
+    generate_camera_ray(L.cam, (float)px + u0, (float)py + u1, l0, l1, o, d);
+    return true;
+}
+
 __global__ void __launch_bounds__(256) k_sppm_cam_generate(SppmLaunch L) {
     for (int st = L.range_begin + blockIdx.x * blockDim.x + threadIdx.x; st < L.range_end; st += gridDim.x * blockDim.x) {
-        int x, y;
-        if (!storage_to_raster(L, st, x, y)) continue;
-        const int pix = y * L.W + x;      // raster index: RNG key
-        const int px = L.film.crop_x0 + x, py = L.film.crop_y0 + y;
-        const uint32_t it = (uint32_t)L.iteration;
-        const float u0 = rng_uniform(L.seed, (uint32_t)pix, it, 0), u1 = rng_uniform(L.seed, (uint32_t)pix, it, 1);
-        float l0 = 0.0f, l1 = 0.0f;
-        if (L.cam.lens_radius > 0.0f) { l0 = rng_uniform(L.seed, (uint32_t)pix, it, 2); l1 = rng_uniform(L.seed, (uint32_t)pix, it, 3); }
+        int pix;
         float3 o, d;
-        generate_camera_ray(L.cam, (float)px + u0, (float)py + u1, l0, l1, o, d);
+        if (!cam_generate_ray(L, st, pix, o, d)) continue;
         const int q = queue_claim(&L.counters[1]);
         L.ro[0][q] = f4(o, TR_INF);
         L.rd[0][q] = f4(d, __int_as_float(st));          // the path carries its STORAGE slot
@@ -94,77 +101,134 @@ __global__ void __launch_bounds__(256) k_sppm_cam_generate(SppmLaunch L) {
     }
 }
 
+// One camera-path vertex (sppm.jl:204-266): direct lighting (a shadow ray into the pass's shadow queue), visible point
+// or continuation.  Returns true when the path continues with (o, d, beta) updated.  Shared by the wavefront kernel
+// (one launch per bounce level) and the path kernel (all levels in one launch), so both compute the same bits.
+__device__ __forceinline__ bool cam_shade_ray(const SppmLaunch& L, int level, float4 h, float3& o, float3& d, float3& beta, int slot, int pix) {
+    if (d.x == 0.0f) d.x = 0.0f;
+    if (d.y == 0.0f) d.y = 0.0f;
+    if (d.z == 0.0f) d.z = 0.0f;
+    const uint32_t prim = __float_as_uint(h.y) - 1u;
+    const float b2 = third_barycentric(L.sc, prim, o, d);
+    const Interaction it = build_interaction(L.sc, prim, o, d, h.z, h.w, b2);
+    const Frame fr = make_frame(it);
+    LobeSet lobes;
+    material_lobes(L.sc.materials[it.material], true, lobes);
+    const float3 wo = -d;
+    const uint32_t dim = 5u + 8u * (uint32_t)(level - 1), itn = (uint32_t)L.iteration;
+    // uniform_sample_one_light + estimate_direct (sppm.jl:503-554); NOT multiplied by beta (Q8)
+    {
+        const int nl = L.sc.n_lights;
+        const float ul = rng_uniform(L.seed, (uint32_t)pix, itn, dim + 0);
+        const int ln = max(1, min((int)ceilf(ul * (float)nl), nl));
+        const float light_pdf = 1.0f / (float)nl;
+        float3 wi, lpos;
+        const float3 Li = sample_li_any(L.sc.lights[ln - 1], it.p, wi, lpos);
+        if (!is_black3(Li)) {
+            const float3 f = bsdf_f(lobes, fr, it.wo, wi, LB_ALL & ~LB_SPECULAR) * fabsf(dot3(wi, it.ns));
+            if (!is_black3(f)) {
+                const float3 contrib = ((f * Li) / 1.0f) / light_pdf;
+                const float3 sdir = lpos - it.p;
+                const int q = queue_claim(&L.counters[32]);
+                if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW_SHADOW] = 1; return false; }
+                L.so[q] = f4(it.p + 1e-6f * sdir, TR_INF);
+                L.sd[q] = f4(sdir, __int_as_float(slot));
+                L.sc_contrib[q] = f4(contrib, 0.0f);
+            }
+        }
+    }
+    const bool is_diffuse = num_components(lobes, LB_DIFFUSE | LB_REFLECTION | LB_TRANSMISSION) > 0;
+    const bool is_glossy = num_components(lobes, LB_GLOSSY | LB_REFLECTION | LB_TRANSMISSION) > 0;
+    if (is_diffuse || (is_glossy && level == L.max_depth)) {
+        const float r = L.tau_r[slot].w;
+        L.vpA[slot] = f4(it.p, r * r);
+        L.vpB[slot] = f4(wo, __uint_as_float(it.material));
+        L.vpC[slot] = f4(fr.ns, is_black3(beta) ? 0.0f : 1.0f);
+        L.vpD[slot] = f4(fr.ss, 0.0f);
+        L.vpE[slot] = f4(fr.ng, 0.0f);
+        return false;
+    }
+    if (level == L.max_depth) return false;
+    const BSDFSample bs = bsdf_sample(lobes, fr, wo, rng_uniform(L.seed, (uint32_t)pix, itn, dim + 5),
+                                      rng_uniform(L.seed, (uint32_t)pix, itn, dim + 6), LB_ALL);
+    if (bs.pdf == 0.0f || is_black3(bs.f)) return false;
+    beta = beta * (bs.f * fabsf(dot3(bs.wi, it.ns)) / bs.pdf);
+    const float by = luminance(beta);
+    if (by < 0.25f) {
+        const float cp = fminf(1.0f, by);
+        if (rng_uniform(L.seed, (uint32_t)pix, itn, dim + 7) > cp) return false;
+        beta = beta / cp;
+    }
+    o = it.p + 1e-6f * bs.wi;
+    d = bs.wi;
+    return true;
+}
+
 __global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level) {
     const int cur = (level - 1) & 1, nxt = level & 1;
     const int n = min(L.counters[level], L.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 h = L.hits[i];
-        const uint32_t prim1 = __float_as_uint(h.y);
-        if (prim1 == 0u) continue;
+        if (__float_as_uint(h.y) == 0u) continue;
         const float4 o4 = L.ro[cur][i], d4 = L.rd[cur][i], w4 = L.rw[cur][i];
-        float3 beta = xyz(w4);
-        float3 d = xyz(d4);
-        if (d.x == 0.0f) d.x = 0.0f;
-        if (d.y == 0.0f) d.y = 0.0f;
-        if (d.z == 0.0f) d.z = 0.0f;
+        float3 o = xyz(o4), d = xyz(d4), beta = xyz(w4);
         const int slot = __float_as_int(d4.w);      // storage slot of the pixel
         const int pix = __float_as_int(w4.w);       // raster index: RNG key
-        const uint32_t prim = prim1 - 1u;
-        const float b2 = third_barycentric(L.sc, prim, xyz(o4), d);
-        const Interaction it = build_interaction(L.sc, prim, xyz(o4), d, h.z, h.w, b2);
-        const Frame fr = make_frame(it);
-        LobeSet lobes;
-        material_lobes(L.sc.materials[it.material], true, lobes);
-        const float3 wo = -d;
-        const uint32_t dim = 5u + 8u * (uint32_t)(level - 1), itn = (uint32_t)L.iteration;
-        // uniform_sample_one_light + estimate_direct (sppm.jl:503-554); NOT multiplied by beta (Q8)
-        {
-            const int nl = L.sc.n_lights;
-            const float ul = rng_uniform(L.seed, (uint32_t)pix, itn, dim + 0);
-            const int ln = max(1, min((int)ceilf(ul * (float)nl), nl));
-            const float light_pdf = 1.0f / (float)nl;
-            float3 wi, lpos;
-            const float3 Li = sample_li_any(L.sc.lights[ln - 1], it.p, wi, lpos);
-            if (!is_black3(Li)) {
-                const float3 f = bsdf_f(lobes, fr, it.wo, wi, LB_ALL & ~LB_SPECULAR) * fabsf(dot3(wi, it.ns));
-                if (!is_black3(f)) {
-                    const float3 contrib = ((f * Li) / 1.0f) / light_pdf;
-                    const float3 sdir = lpos - it.p;
-                    const int q = queue_claim(&L.counters[32]);
-                    if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW_SHADOW] = 1; continue; }
-                    L.so[q] = f4(it.p + 1e-6f * sdir, TR_INF);
-                    L.sd[q] = f4(sdir, __int_as_float(slot));
-                    L.sc_contrib[q] = f4(contrib, 0.0f);
-                }
-            }
-        }
-        const bool is_diffuse = num_components(lobes, LB_DIFFUSE | LB_REFLECTION | LB_TRANSMISSION) > 0;
-        const bool is_glossy = num_components(lobes, LB_GLOSSY | LB_REFLECTION | LB_TRANSMISSION) > 0;
-        if (is_diffuse || (is_glossy && level == L.max_depth)) {
-            const float r = L.tau_r[slot].w;
-            L.vpA[slot] = f4(it.p, r * r);
-            L.vpB[slot] = f4(wo, __uint_as_float(it.material));
-            L.vpC[slot] = f4(fr.ns, is_black3(beta) ? 0.0f : 1.0f);
-            L.vpD[slot] = f4(fr.ss, 0.0f);
-            L.vpE[slot] = f4(fr.ng, 0.0f);
-            continue;
-        }
-        if (level == L.max_depth) continue;
-        const BSDFSample bs = bsdf_sample(lobes, fr, wo, rng_uniform(L.seed, (uint32_t)pix, itn, dim + 5),
-                                          rng_uniform(L.seed, (uint32_t)pix, itn, dim + 6), LB_ALL);
-        if (bs.pdf == 0.0f || is_black3(bs.f)) continue;
-        beta = beta * (bs.f * fabsf(dot3(bs.wi, it.ns)) / bs.pdf);
-        const float by = luminance(beta);
-        if (by < 0.25f) {
-            const float cp = fminf(1.0f, by);
-            if (rng_uniform(L.seed, (uint32_t)pix, itn, dim + 7) > cp) continue;
-            beta = beta / cp;
-        }
+        if (!cam_shade_ray(L, level, h, o, d, beta, slot, pix)) continue;
         const int q = queue_claim(&L.counters[level + 1]);
-        L.ro[nxt][q] = f4(it.p + 1e-6f * bs.wi, TR_INF);
-        L.rd[nxt][q] = f4(bs.wi, __int_as_float(slot));
+        L.ro[nxt][q] = f4(o, TR_INF);
+        L.rd[nxt][q] = f4(d, __int_as_float(slot));
         L.rw[nxt][q] = f4(beta, __int_as_float(pix));
     }
+}
+
+// Path kernel: one thread carries one camera path through its first `path_levels` bounces - generate, then (closest hit
+// -> vertex) - without ray queues in HBM; the paths that are still alive afterwards enter the wavefront queues of the next
+// level.  Measured (profiles/r2_experiments.md): carrying paths through ALL levels in one kernel is 1.7-3x SLOWER than the
+// wavefront (only the few lanes whose path hit glass stay alive at deeper levels, un-compacted: 3-10 of 32 lanes walk
+// the 600-node glass block), so the default is path_levels = 1: the level where every lane has a ray - generate, extend
+// and shade of the largest level in one launch, no primary-ray / hit queues - and compacted queues from level 2 on.
+// Every vertex goes through cam_shade_ray, so visible points and shadow rays are those of the wavefront kernels.
+#ifndef TR_PATH_MIN_BLOCKS
+#define TR_PATH_MIN_BLOCKS 6
+#endif
+static __device__ __noinline__ bool cam_vertex(const SppmLaunch& L, int level, float4 h, float3& o, float3& d, float3& beta, int slot, int pix) {
+    return cam_shade_ray(L, level, h, o, d, beta, slot, pix);
+}
+static __device__ __noinline__ bool cam_first_ray(const SppmLaunch& L, int st, int& pix, float3& o, float3& d) {
+    return cam_generate_ray(L, st, pix, o, d);
+}
+template <int SLAB, bool COUNT, int WAIT>
+__global__ void __launch_bounds__(128, TR_PATH_MIN_BLOCKS) k_sppm_cam_path(const __grid_constant__ SppmLaunch L, int path_levels, int* error_flag) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned n_rays = 0;
+    for (int base = L.range_begin + blockIdx.x * blockDim.x + (threadIdx.x - lane); base < L.range_end; base += gridDim.x * blockDim.x) {
+        const int st = base + lane;
+        int pix = 0;
+        float3 o = f3s(0.0f), d = f3s(1.0f), beta = f3s(1.0f);
+        bool alive = st < L.range_end && cam_first_ray(L, st, pix, o, d);
+        const int last = min(L.max_depth, path_levels);
+        for (int level = 1; level <= last; ++level) {
+            __syncwarp();                                         // reconverge before the walk (see k_wh_primary)
+            if (!__any_sync(full, alive)) break;
+            HitRecord h;
+            traverse_any<SLAB, false, COUNT, WAIT>(L.sc, alive, o, d, TR_INF, h, L.stats + ST_NODES, error_flag);
+            if (alive) {
+                n_rays++;
+                alive = h.prim != 0u && cam_vertex(L, level, make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1), o, d, beta, st, pix);
+            }
+        }
+        if (alive && last < L.max_depth) {                        // the rest of the path goes through the wavefront queues
+            const int q = queue_claim(&L.counters[last + 1]);
+            L.ro[last & 1][q] = f4(o, TR_INF);
+            L.rd[last & 1][q] = f4(d, __int_as_float(st));
+            L.rw[last & 1][q] = f4(beta, __int_as_float(pix));
+        }
+    }
+    __syncwarp();
+    n_rays = __reduce_add_sync(full, n_rays);
+    if (lane == 0 && n_rays) atomicAdd(&L.stats[ST_RAYS_EXTEND], (unsigned long long)n_rays);
 }
 
 // ---------------------------------------------------------------- grid build (sppm.jl:278-318)
@@ -312,38 +376,82 @@ __global__ void k_grid_check(SppmLaunch L) {
 }
 
 // ---------------------------------------------------------------- photon pass (sppm.jl:320-436)
+// photon j of this launch: light choice, direction and initial beta (sppm.jl:334-360).  False: the photon carries nothing.
+__device__ __forceinline__ bool photon_generate_ray(const SppmLaunch& L, int j, float3& o, float3& d, float3& beta) {
+    const unsigned long long hidx = (unsigned long long)(L.iteration - 1) * (unsigned long long)L.photons_per_iteration +
+                                    (unsigned long long)(L.photon_begin + j);
+    // light choice: sample_discrete(light_distribution, halton dim 0), sampling.jl:32-41
+    const float ls = radical_inverse(0, hidx);
+    const int nl = L.sc.n_lights;
+    int last = -1;
+    for (int k = 0; k <= nl; ++k) if (L.light_cdf[k] <= ls) last = k;
+    const int ln = min(max(last, 0), nl - 1);
+    const float light_pdf = L.light_func_int > 0.0f ? L.light_func[ln] / (L.light_func_int * (float)nl) : 0.0f;
+    const DeviceLight& light = L.sc.lights[ln];
+    const float u0 = radical_inverse(1, hidx), u1 = radical_inverse(2, hidx);
+    // sample_le (point.jl:60-69, spot.jl:46-55)
+    float3 le;
+    float pdf_dir;
+    const float3 I = f3(light.I[0], light.I[1], light.I[2]);
+    if (light.kind == TRACE_LIGHT_POINT) { d = uniform_sphere(u0, u1); pdf_dir = 1.0f / (4.0f * TR_PI); le = I; }
+    else {
+        d = xform_vector(light.m, uniform_cone(u0, u1, light.cos_total));
+        pdf_dir = 1.0f / (2.0f * TR_PI * (1.0f - light.cos_total));
+        le = I * spot_falloff(light, d);
+    }
+    const float pdf_pos = 1.0f;
+    if (pdf_dir == 0.0f || is_black3(le)) return false;
+    beta = (fabsf(dot3(d, d)) * le) / (light_pdf * pdf_pos * pdf_dir);      // light_normal == ray.d
+    if (is_black3(beta)) return false;
+    o = f3(light.pos[0], light.pos[1], light.pos[2]);
+    return true;
+}
+
 __global__ void __launch_bounds__(256) k_photon_generate(SppmLaunch L) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L.n_photons; j += gridDim.x * blockDim.x) {
-        const unsigned long long hidx = (unsigned long long)(L.iteration - 1) * (unsigned long long)L.photons_per_iteration +
-                                        (unsigned long long)(L.photon_begin + j);
-        // light choice: sample_discrete(light_distribution, halton dim 0), sampling.jl:32-41
-        const float ls = radical_inverse(0, hidx);
-        const int nl = L.sc.n_lights;
-        int last = -1;
-        for (int k = 0; k <= nl; ++k) if (L.light_cdf[k] <= ls) last = k;
-        const int ln = min(max(last, 0), nl - 1);
-        const float light_pdf = L.light_func_int > 0.0f ? L.light_func[ln] / (L.light_func_int * (float)nl) : 0.0f;
-        const DeviceLight& light = L.sc.lights[ln];
-        const float u0 = radical_inverse(1, hidx), u1 = radical_inverse(2, hidx);
-        // sample_le (point.jl:60-69, spot.jl:46-55)
-        float3 d, le;
-        float pdf_dir;
-        const float3 I = f3(light.I[0], light.I[1], light.I[2]);
-        if (light.kind == TRACE_LIGHT_POINT) { d = uniform_sphere(u0, u1); pdf_dir = 1.0f / (4.0f * TR_PI); le = I; }
-        else {
-            d = xform_vector(light.m, uniform_cone(u0, u1, light.cos_total));
-            pdf_dir = 1.0f / (2.0f * TR_PI * (1.0f - light.cos_total));
-            le = I * spot_falloff(light, d);
-        }
-        const float pdf_pos = 1.0f;
-        if (pdf_dir == 0.0f || is_black3(le)) continue;
-        const float3 beta = (fabsf(dot3(d, d)) * le) / (light_pdf * pdf_pos * pdf_dir);      // light_normal == ray.d
-        if (is_black3(beta)) continue;
+        float3 o, d, beta;
+        if (!photon_generate_ray(L, j, o, d, beta)) continue;
         const int q = queue_claim(&L.counters[1]);
-        L.ro[0][q] = f4(f3(light.pos[0], light.pos[1], light.pos[2]), TR_INF);
+        L.ro[0][q] = f4(o, TR_INF);
         L.rd[0][q] = f4(d, __int_as_float(j));
         L.rw[0][q] = f4(beta, luminance(beta));
     }
+}
+
+// One photon-path vertex (sppm.jl:362-434): a deposit request at depth > 1, then the continuation.  beta is NOT updated
+// along the path (Q7); `lum0` = Y(beta).  Returns true when the photon flies on with (o, d) updated.
+__device__ __forceinline__ bool photon_shade_ray(const SppmLaunch& L, int level, float4 h, float3& o, float3& d, float3 beta, float lum0, int j) {
+    if (d.x == 0.0f) d.x = 0.0f;
+    if (d.y == 0.0f) d.y = 0.0f;
+    if (d.z == 0.0f) d.z = 0.0f;
+    const uint32_t prim = __float_as_uint(h.y) - 1u;
+    const float b2 = third_barycentric(L.sc, prim, o, d);
+    const Interaction it = build_interaction(L.sc, prim, o, d, h.z, h.w, b2);
+    const float3 wo = -d;
+    if (level > 1) {
+        // photon landed at depth > 1: queue a deposit request for k_photon_deposit (sppm.jl:377-403).  The grid is
+        // NOT consulted here - it is being rebuilt by the concurrent camera pass; the deposit kernel does the lookup
+        const int q = queue_claim(&L.counters[32]);
+        if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW_DEPOSIT] = 1; return false; }
+        L.so[q] = f4(it.p, 0.0f);
+        L.sd[q] = f4(wo, 0.0f);
+        L.sc_contrib[q] = f4(beta, 0.0f);
+    }
+    const Frame fr = make_frame(it);
+    LobeSet lobes;
+    material_lobes(L.sc.materials[it.material], true, lobes);
+    const unsigned long long hidx = (unsigned long long)(L.iteration - 1) * (unsigned long long)L.photons_per_iteration +
+                                    (unsigned long long)(L.photon_begin + j);
+    const int hdim = 6 + 3 * (level - 1);
+    const BSDFSample bs = bsdf_sample(lobes, fr, wo, radical_inverse(hdim, hidx), radical_inverse(hdim + 1, hidx), LB_ALL);
+    if (is_black3(bs.f) || bs.pdf == 0.0f) return false;
+    const float3 beta_new = ((beta * bs.f) * fabsf(dot3(bs.wi, it.ns))) / bs.pdf;
+    const float q = fmaxf(0.0f, 1.0f - luminance(beta_new) / lum0);
+    if (radical_inverse(hdim + 2, hidx) < q) return false;
+    if (level + 1 > L.max_depth) return false;
+    o = it.p + 1e-6f * bs.wi;
+    d = bs.wi;
+    return true;
 }
 
 __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
@@ -351,45 +459,55 @@ __global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
     const int n = min(L.counters[level], L.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 h = L.hits[i];
-        const uint32_t prim1 = __float_as_uint(h.y);
-        if (prim1 == 0u) continue;
+        if (__float_as_uint(h.y) == 0u) continue;
         const float4 o4 = L.ro[cur][i], d4 = L.rd[cur][i], w4 = L.rw[cur][i];
-        const float3 beta = xyz(w4);
-        float3 d = xyz(d4);
-        if (d.x == 0.0f) d.x = 0.0f;
-        if (d.y == 0.0f) d.y = 0.0f;
-        if (d.z == 0.0f) d.z = 0.0f;
-        const uint32_t prim = prim1 - 1u;
-        const float b2 = third_barycentric(L.sc, prim, xyz(o4), d);
-        const Interaction it = build_interaction(L.sc, prim, xyz(o4), d, h.z, h.w, b2);
-        const float3 wo = -d;
-        if (level > 1) {
-            // photon landed at depth > 1: queue a deposit request for k_photon_deposit (sppm.jl:377-403).  The grid is
-            // NOT consulted here - it is being rebuilt by the concurrent camera pass; the deposit kernel does the lookup
-            const int q = queue_claim(&L.counters[32]);
-            if (q >= L.cap_shadow) { L.flags[IC_OVERFLOW_DEPOSIT] = 1; continue; }
-            L.so[q] = f4(it.p, 0.0f);
-            L.sd[q] = f4(wo, 0.0f);
-            L.sc_contrib[q] = f4(beta, 0.0f);
-        }
-        const Frame fr = make_frame(it);
-        LobeSet lobes;
-        material_lobes(L.sc.materials[it.material], true, lobes);
-        const int j = __float_as_int(d4.w);
-        const unsigned long long hidx = (unsigned long long)(L.iteration - 1) * (unsigned long long)L.photons_per_iteration +
-                                        (unsigned long long)(L.photon_begin + j);
-        const int hdim = 6 + 3 * (level - 1);
-        const BSDFSample bs = bsdf_sample(lobes, fr, wo, radical_inverse(hdim, hidx), radical_inverse(hdim + 1, hidx), LB_ALL);
-        if (is_black3(bs.f) || bs.pdf == 0.0f) continue;
-        const float3 beta_new = ((beta * bs.f) * fabsf(dot3(bs.wi, it.ns))) / bs.pdf;
-        const float q = fmaxf(0.0f, 1.0f - luminance(beta_new) / w4.w);
-        if (radical_inverse(hdim + 2, hidx) < q) continue;
-        if (level + 1 > L.max_depth) continue;
+        float3 o = xyz(o4), d = xyz(d4);
+        if (!photon_shade_ray(L, level, h, o, d, xyz(w4), w4.w, __float_as_int(d4.w))) continue;
         const int qi = queue_claim(&L.counters[level + 1]);
-        L.ro[nxt][qi] = f4(it.p + 1e-6f * bs.wi, TR_INF);
-        L.rd[nxt][qi] = f4(bs.wi, d4.w);
+        L.ro[nxt][qi] = f4(o, TR_INF);
+        L.rd[nxt][qi] = f4(d, d4.w);
         L.rw[nxt][qi] = w4;                                      // beta is NOT updated (Q7)
     }
+}
+
+// photon path kernel: see k_sppm_cam_path
+static __device__ __noinline__ bool photon_vertex(const SppmLaunch& L, int level, float4 h, float3& o, float3& d, float3 beta, float lum0, int j) {
+    return photon_shade_ray(L, level, h, o, d, beta, lum0, j);
+}
+static __device__ __noinline__ bool photon_first_ray(const SppmLaunch& L, int j, float3& o, float3& d, float3& beta) {
+    return photon_generate_ray(L, j, o, d, beta);
+}
+template <int SLAB, bool COUNT, int WAIT>
+__global__ void __launch_bounds__(128, TR_PATH_MIN_BLOCKS) k_photon_path(const __grid_constant__ SppmLaunch L, int path_levels, int* error_flag) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned n_rays = 0;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < L.n_photons; base += gridDim.x * blockDim.x) {
+        const int j = base + lane;
+        float3 o = f3s(0.0f), d = f3s(1.0f), beta = f3s(0.0f);
+        bool alive = j < L.n_photons && photon_first_ray(L, j, o, d, beta);
+        const float lum0 = luminance(beta);
+        const int last = min(L.max_depth, path_levels);
+        for (int level = 1; level <= last; ++level) {
+            __syncwarp();
+            if (!__any_sync(full, alive)) break;
+            HitRecord h;
+            traverse_any<SLAB, false, COUNT, WAIT>(L.sc, alive, o, d, TR_INF, h, L.stats + ST_NODES, error_flag);
+            if (alive) {
+                n_rays++;
+                alive = h.prim != 0u && photon_vertex(L, level, make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1), o, d, beta, lum0, j);
+            }
+        }
+        if (alive && last < L.max_depth) {
+            const int q = queue_claim(&L.counters[last + 1]);
+            L.ro[last & 1][q] = f4(o, TR_INF);
+            L.rd[last & 1][q] = f4(d, __int_as_float(j));
+            L.rw[last & 1][q] = f4(beta, lum0);
+        }
+    }
+    __syncwarp();
+    n_rays = __reduce_add_sync(full, n_rays);
+    if (lane == 0 && n_rays) atomicAdd(&L.stats[ST_RAYS_EXTEND], (unsigned long long)n_rays);
 }
 
 // One WARP per deposit request: the 32 lanes stride over the hashed cell's CSR list (coalesced index loads), test
@@ -690,24 +808,46 @@ static int sppm_camera_lane(trace_ctx* c, SppmState* s, int l, int iteration) {
     TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), st));
     TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), st)); c->work_slot = 0;
     const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
-    c->kev_begin(TRACE_K_GENERATE);
-    k_sppm_cam_generate<<<g_stream, 256, 0, st>>>(W);
-    c->kev_end();
-    c->stats.kernel_launches++;
-    for (int level = 1; level <= W.max_depth; ++level) {
-        const int cur = (level - 1) & 1;
-        c->cur_level = level;
-        launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
-                      stats + ST_NODES, W.flags + IC_ERROR);
-        c->kev_begin(TRACE_K_SHADE);
-        k_sppm_cam_shade<<<occupancy_grid(c, k_sppm_cam_shade, 128), 128, 0, st>>>(W, level);
+    const bool path = c->sppm_path && c->slab != 1;
+    if (path) {
+        // all bounce levels of the camera paths in ONE launch (k_sppm_cam_path); rays are counted by the kernel itself
+        c->kev_begin(TRACE_K_EXTEND);
+        trav_dispatch(c, [&](auto S, auto C_, auto Wk) {
+            auto k = k_sppm_cam_path<decltype(S)::value, decltype(C_)::value, decltype(Wk)::value>;
+            k<<<occupancy_grid(c, k, 128), 128, 0, st>>>(W, c->sppm_path, W.flags + IC_ERROR);
+        });
         c->kev_end();
         c->stats.kernel_launches++;
+        for (int level = c->sppm_path + 1; level <= W.max_depth; ++level) {
+            const int cur = (level - 1) & 1;
+            c->cur_level = level;
+            launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
+                          stats + ST_NODES, W.flags + IC_ERROR);
+            c->kev_begin(TRACE_K_SHADE);
+            k_sppm_cam_shade<<<occupancy_grid(c, k_sppm_cam_shade, 128), 128, 0, st>>>(W, level);
+            c->kev_end();
+            c->stats.kernel_launches++;
+        }
+    } else {
+        c->kev_begin(TRACE_K_GENERATE);
+        k_sppm_cam_generate<<<g_stream, 256, 0, st>>>(W);
+        c->kev_end();
+        c->stats.kernel_launches++;
+        for (int level = 1; level <= W.max_depth; ++level) {
+            const int cur = (level - 1) & 1;
+            c->cur_level = level;
+            launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
+                          stats + ST_NODES, W.flags + IC_ERROR);
+            c->kev_begin(TRACE_K_SHADE);
+            k_sppm_cam_shade<<<occupancy_grid(c, k_sppm_cam_shade, 128), 128, 0, st>>>(W, level);
+            c->kev_end();
+            c->stats.kernel_launches++;
+        }
     }
     // shadow rays of all levels in one any-hit launch (they only feed Ld)
     launch_shadow(c, g_trav, W.sc, (const float4*)W.so, (const float4*)W.sd, (const float4*)W.sc_contrib,
                   (const int*)(ic + 32), W.cap_shadow, W.Ld, stats + ST_NODES, W.flags + IC_ERROR);
-    k_sppm_stats<<<1, 32, 0, st>>>(ic, stats, W.max_depth, W.cap, 1);
+    k_sppm_stats<<<1, 32, 0, st>>>(ic, stats, W.max_depth, W.cap, 1);      // (levels run by the path kernel have counter 0: it counts its own rays)
     c->stats.kernel_launches++;
     return 0;
 }
@@ -790,6 +930,26 @@ static int sppm_trace_lane(trace_ctx* c, SppmState* s, int j, int iteration, int
     TR_CUDA(c, cudaMemsetAsync(ic, 0, 60 * sizeof(int), st));
     TR_CUDA(c, cudaMemsetAsync(ic + 64, 0, 64 * sizeof(int), st)); c->work_slot = 0;
     const int g_stream = persistent_grid(c, 8), g_trav = persistent_grid(c, 16);
+    if (c->sppm_path && c->slab != 1) {
+        c->kev_begin(TRACE_K_EXTEND);
+        trav_dispatch(c, [&](auto S, auto C_, auto Wk) {
+            auto k = k_photon_path<decltype(S)::value, decltype(C_)::value, decltype(Wk)::value>;
+            k<<<occupancy_grid(c, k, 128), 128, 0, st>>>(W, c->sppm_path, W.flags + IC_ERROR);
+        });
+        c->kev_end();
+        c->stats.kernel_launches++;
+        for (int level = c->sppm_path + 1; level <= W.max_depth; ++level) {
+            const int cur = (level - 1) & 1;
+            c->cur_level = level;
+            launch_extend(c, g_trav, W.sc, (const float4*)W.ro[cur], (const float4*)W.rd[cur], (const int*)(ic + level), W.cap, W.hits,
+                          stats + ST_NODES, W.flags + IC_ERROR);
+            c->kev_begin(TRACE_K_SHADE);
+            k_photon_shade<<<occupancy_grid(c, k_photon_shade, 128), 128, 0, st>>>(W, level);
+            c->kev_end();
+            c->stats.kernel_launches++;
+        }
+        return 0;
+    }
     c->kev_begin(TRACE_K_GENERATE);
     k_photon_generate<<<g_stream, 256, 0, st>>>(W);
     c->kev_end();

@@ -24,11 +24,11 @@ __global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_extend(DeviceSce
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += gridDim.x * blockDim.x) {
         const int i = base + lane;
         const bool valid = i < n;
-        const float4 o = valid ? ro[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = valid ? rd[i] : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        const float4 o = valid ? q_load(&ro[i]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = valid ? q_load(&rd[i]) : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         HitRecord h;
         // closest hit; the third barycentric is rebuilt exactly in the shade stage from the winning triangle
         traverse_any<SLAB, false, COUNT, WAIT>(sc, valid, xyz(o), xyz(d), o.w, h, counters, error_flag);
-        if (valid) hits[i] = make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1);
+        if (valid) q_store(&hits[i], make_float4(h.t, __uint_as_float(h.prim), h.b0, h.b1));
     }
 }
 
@@ -41,10 +41,10 @@ __global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_shadow(DeviceSce
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += gridDim.x * blockDim.x) {
         const int i = base + lane;
         const bool valid = i < n;
-        const float4 o = valid ? so[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = valid ? sd[i] : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        const float4 o = valid ? q_load(&so[i]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = valid ? q_load(&sd[i]) : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         HitRecord h;
         if (!traverse_any<SLAB, true, COUNT, WAIT>(sc, valid, xyz(o), xyz(d), o.w, h, counters, error_flag) && valid) {
-            const float4 c = contrib[i];
+            const float4 c = q_load(&contrib[i]);
             atomicAdd(&accum[__float_as_int(d.w)], make_float4(c.x, c.y, c.z, 0.0f));   // 128-bit vector atomic (sm_90+)
         }
     }

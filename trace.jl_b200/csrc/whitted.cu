@@ -134,21 +134,24 @@ __global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_primary(const __
         traverse_any<SLAB, false, false, WAIT>(L.sc, valid, o, d, TR_INF, h, nullptr, error_flag);
         if (i < L.n_slots) {
             L.accum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            L.hits[i] = make_float4(h.t, __uint_as_float(valid ? h.prim : 0u), h.b0, h.b1);
+            q_store(&L.hits[i], make_float4(h.t, __uint_as_float(valid ? h.prim : 0u), h.b0, h.b1));
         }
         n_active += __popc(__ballot_sync(0xffffffffu, valid));
     }
     if (lane == 0 && n_active) atomicAdd(&L.counters[1], n_active);     // rays traced at level 1 (statistics only)
 }
 
-__global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
+#ifndef TR_SHADE_MIN_BLOCKS
+#define TR_SHADE_MIN_BLOCKS 8      // 64 registers: the shade kernels wait on scattered primitive / normal fetches, occupancy beats registers (22.75 -> 22.57 ms)
+#endif
+__global__ void __launch_bounds__(128, TR_SHADE_MIN_BLOCKS) k_wh_shade(WhittedLaunch L, int level) {
     const int cur = (level - 1) & 1, nxt = level & 1;
     const bool rederive = L.fused && level == 1;
     const int n = rederive ? L.n_slots : min(L.counters[level], L.cap_rays);
     if (level == 1 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&L.stats[ST_PRIMARY_RAYS], (unsigned long long)L.counters[1]);
     unsigned n_hit = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 h = L.hits[i];
+        const float4 h = q_load(&L.hits[i]);                // queues are streamed once: keep them out of the way of the BVH in L2
         const uint32_t prim1 = __float_as_uint(h.y);
         if (prim1 == 0u) continue;                          // miss: le(light, ray) == 0 (lights/light.jl:41)
         n_hit++;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
             float3 o, dd;
             slot_camera_ray(L.frame->cam, L.frame->seed, pix, s, fx, fy, o, dd);
             o4 = f4(o, TR_INF); d4 = f4(dd, __int_as_float(i)); w = f3s(1.0f);
-        } else { o4 = L.ro[cur][i]; d4 = L.rd[cur][i]; w = xyz(L.rw[cur][i]); }
+        } else { o4 = q_load(&L.ro[cur][i]); d4 = q_load(&L.rd[cur][i]); w = xyz(q_load(&L.rw[cur][i])); }
         float3 d = xyz(d4);
         if (d.x == 0.0f) d.x = 0.0f;                        // the ray as intersect! left it (check_direction!)
         if (d.y == 0.0f) d.y = 0.0f;
@@ -184,9 +187,9 @@ __global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
             const float3 sdir = lpos - it.p;                 // spawn_ray(p0, p1): un-normalised, t_max = Inf (Q5)
             const int q = queue_claim(&L.counters[32]);
             if (q < L.cap_shadow) {
-                L.so[q] = f4(it.p + 1e-6f * sdir, TR_INF);
-                L.sd[q] = f4(sdir, d4.w);
-                L.sc_contrib[q] = f4(contrib, 0.0f);
+                q_store(&L.so[q], f4(it.p + 1e-6f * sdir, TR_INF));
+                q_store(&L.sd[q], f4(sdir, d4.w));
+                q_store(&L.sc_contrib[q], f4(contrib, 0.0f));
             } else L.counters[IC_OVERFLOW] = 1;
         }
         if (level + 1 <= L.max_depth) {
@@ -200,9 +203,9 @@ __global__ void __launch_bounds__(128) k_wh_shade(WhittedLaunch L, int level) {
                 const float3 wn = w * (bs.f * adot / bs.pdf);
                 const int q = queue_claim(&L.counters[level + 1]);
                 if (q < L.cap_rays) {
-                    L.ro[nxt][q] = f4(it.p + 1e-6f * bs.wi, TR_INF);     // spawn_ray(si, wi), Trace.jl:206-211
-                    L.rd[nxt][q] = f4(bs.wi, d4.w);
-                    L.rw[nxt][q] = f4(wn, 0.0f);
+                    q_store(&L.ro[nxt][q], f4(it.p + 1e-6f * bs.wi, TR_INF));     // spawn_ray(si, wi), Trace.jl:206-211
+                    q_store(&L.rd[nxt][q], f4(bs.wi, d4.w));
+                    q_store(&L.rw[nxt][q], f4(wn, 0.0f));
                 } else L.counters[IC_OVERFLOW] = 1;
             }
         }
@@ -290,7 +293,46 @@ __global__ void __launch_bounds__(256) k_wh_splat(WhittedLaunch L) {
         const int wnx = (int)(floorf((float)px + 0.5f + F.rx) + 1.0f - wx0) + 1, wny = (int)(floorf((float)py + 0.5f + F.ry) + 1.0f - wy0) + 1;
         const int n_targets = __shfl_sync(full, valid ? wnx * wny : 0, gbase);
         const int n_loop = max(__shfl_sync(full, n_targets, 0), __shfl_sync(full, n_targets, 16));     // warp-uniform trip count
-        for (int j0 = 0; j0 < n_loop; j0 += 16) {
+        const bool packed = __all_sync(full, wnx <= 6 && wny <= 6);
+        if (packed) {
+            // Every lane works out ONCE, for its own sample, which filter-table column / row each window column / row
+            // gets (0: outside the sample's footprint) - 5 bits each - so a target lane needs two shuffles and a table
+            // lookup per sample instead of redoing the footprint arithmetic 16 x 16 times per pixel.
+            const float p0x = fmaxf(ceilf(dx - F.rx), c.x0), p0y = fmaxf(ceilf(dy - F.ry), c.y0);
+            const float p1x = fminf(floorf(dx + F.rx) + 1.0f, c.x1), p1y = fminf(floorf(dy + F.ry) + 1.0f, c.y1);
+            unsigned colbits = 0u, rowbits = 0u;
+            #pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const float x = wx0 + (float)k, y = wy0 + (float)k;
+                if (valid && k < wnx && x >= p0x && x <= p1x)
+                    colbits |= (unsigned)(int)clampf(ceilf(fabsf((x - dx) * F.inv_rx * 16.0f)), 1.0f, 16.0f) << (5 * k);
+                if (valid && k < wny && y >= p0y && y <= p1y)
+                    rowbits |= (unsigned)(int)clampf(floorf(fabsf((y - dy) * F.inv_ry * 16.0f)), 1.0f, 16.0f) << (5 * k);
+            }
+            for (int j0 = 0; j0 < n_loop; j0 += 16) {
+                const int j = j0 + g;
+                const int tyi = j / wnx, txi = j - tyi * wnx;
+                float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                bool any = false;
+                #pragma unroll 4
+                for (int k = 0; k < 16; ++k) {
+                    const int src = gbase + k;
+                    const unsigned cb = __shfl_sync(full, colbits, src), rb = __shfl_sync(full, rowbits, src);
+                    const float ar = __shfl_sync(full, a.x, src), ag = __shfl_sync(full, a.y, src), ab = __shfl_sync(full, a.z, src);
+                    const unsigned ox = (cb >> (5 * txi)) & 31u, oy = (rb >> (5 * tyi)) & 31u;
+                    if (j < n_targets && ox != 0u && oy != 0u) {
+                        const float wgt = __ldg(&F.table[(oy - 1u) * 16u + (ox - 1u)]);
+                        acc.x += ar * wgt; acc.y += ag * wgt; acc.z += ab * wgt; acc.w += wgt; any = true;
+                    }
+                }
+                if (any) {
+                    const int ix = (int)wx0 + txi - F.crop_x0, iy = (int)wy0 + tyi - F.crop_y0;
+                    atomicAdd(&L.film_rgbw[(size_t)iy * F.width + ix], acc);
+                }
+            }
+            continue;
+        }
+        for (int j0 = 0; j0 < n_loop; j0 += 16) {          // wide filters: per-(sample, target) footprint arithmetic
             const int j = j0 + g;
             const float x = wx0 + (float)(j % wnx), y = wy0 + (float)(j / wnx);
             float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
