@@ -13,11 +13,16 @@
 // Compiled with -ffp-contract=off: the cost arithmetic must round like the reference's.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <limits>
 #include <cstdlib>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -72,16 +77,61 @@ struct Box {
 };
 
 // ------------------------------------------------------------------ parallel helpers
-// A fork-join over [0, n) in `parts` contiguous chunks on std::threads (the build runs a few hundred of these).
+// A fork-join over [0, n) in `parts` contiguous chunks.  The build runs a few thousand of these, so the workers are a
+// persistent pool (one per process, grown on demand) woken through a condition variable, not threads spawned per call.
+class ChunkPool {
+  public:
+    static ChunkPool& get() { static ChunkPool p; return p; }
+    template <class F>
+    void run(int64_t n, int parts, F f) {
+        if (parts <= 1 || n < 2) { f(0, (int64_t)0, n); return; }
+        std::unique_lock<std::mutex> entry(entry_mutex_);            // one fork-join at a time (builds may come from several host threads)
+        grow(parts - 1);
+        std::function<void(int)> job = [&](int p) { f(p, n * p / parts, n * (p + 1) / parts); };
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &job; parts_ = parts; next_ = 1; pending_ = parts - 1; ++epoch_;
+        }
+        cv_.notify_all();
+        f(0, (int64_t)0, n / parts);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+    ~ChunkPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++epoch_; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+  private:
+    void grow(int n) {
+        while ((int)workers_.size() < n) workers_.emplace_back([this] { loop(); });
+    }
+    void loop() {
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return stop_ || (job_ != nullptr && next_ < parts_); });
+            if (stop_) return;
+            while (job_ != nullptr && next_ < parts_) {
+                const int p = next_++;
+                const std::function<void(int)>* job = job_;
+                lk.unlock();
+                (*job)(p);
+                lk.lock();
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::mutex entry_mutex_, m_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(int)>* job_ = nullptr;
+    int parts_ = 0, next_ = 0, pending_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
 template <class F>
-void parallel_chunks(int64_t n, int parts, F f) {
-    if (parts <= 1 || n < 2) { f(0, (int64_t)0, n); return; }
-    std::vector<std::thread> th;
-    th.reserve((size_t)parts - 1);
-    for (int p = 1; p < parts; ++p) th.emplace_back([=]() { f(p, n * p / parts, n * (p + 1) / parts); });
-    f(0, (int64_t)0, n / parts);
-    for (auto& t : th) t.join();
-}
+void parallel_chunks(int64_t n, int parts, F f) { ChunkPool::get().run(n, parts, f); }
 
 int build_threads() {
     const char* e = getenv("TRACE_BVH_THREADS");
@@ -330,9 +380,13 @@ int build_subtree(const Splitter& split, const uint32_t* perm, int64_t from, int
 // kTopThreshold primitives are set aside as jobs; (2) the jobs in parallel (disjoint ranges of the permutation);
 // (3) stitch: item sizes -> preorder slots by a prefix sum, local indices rebased.  The result is the array the
 // one-threaded build produces, bit for bit (tests/test_bvh_build.py compares them).
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 template <class Splitter>
 int build_tree(Splitter split, uint32_t* perm, int64_t n, trace_bvh* bvh) {
     const int threads = build_threads();
+    const bool prof = getenv("TRACE_BVH_PROFILE") != nullptr;
+    const double t_begin = now_s();
     struct Item { int kind; trace_bvh_node node; int64_t from, to; int64_t second_item; int job; };   // kind 0 interior, 1 leaf, 2 job
     std::vector<Item> items;
     std::vector<std::pair<int64_t, int64_t>> jobs;
@@ -366,6 +420,7 @@ int build_tree(Splitter split, uint32_t* perm, int64_t n, trace_bvh* bvh) {
             todo.push_back({t.from, s.mid, -1});
         }
     }
+    const double t_top = now_s();
     std::vector<LocalTree> local(jobs.size());
     std::vector<int> rcs(jobs.size(), 0);
     {
@@ -387,6 +442,7 @@ int build_tree(Splitter split, uint32_t* perm, int64_t n, trace_bvh* bvh) {
         for (auto& t : th) t.join();
     }
     for (int rc : rcs) if (rc) return rc;
+    const double t_jobs = now_s();
     // stitch
     std::vector<int64_t> node_base(items.size() + 1, 0), order_base(items.size() + 1, 0);
     for (size_t i = 0; i < items.size(); ++i) {
@@ -421,6 +477,8 @@ int build_tree(Splitter split, uint32_t* perm, int64_t n, trace_bvh* bvh) {
             }
         }
     });
+    if (prof) fprintf(stderr, "bvh build: %d threads, top phase %.2f s (%zu items, %zu jobs), jobs %.2f s, stitch %.2f s\n", threads, t_top - t_begin,
+                      items.size(), jobs.size(), t_jobs - t_top, now_s() - t_jobs);
     return 0;
 }
 

@@ -28,6 +28,8 @@ struct SppmLaunch {
     int max_depth, iteration;
     uint64_t seed;
     int W, H, npix;            // npix = W*H is also the hash-table size (sppm.jl:141)
+    unsigned long long hash_magic;   // h % npix without a 64-bit division: q = mulhi(h, magic) >> shift (grid_hash)
+    int hash_shift;                  // < 0: tables of <= 64 cells take the plain modulo
     // pixel STORAGE order (all per-pixel arrays): image rows are dealt round-robin to `world` ranks and each rank's rows
     // are contiguous, padded to chunk_rows rows - so a rank's visible points are one slice that an all-gather can move.
     // world == 1: storage index == raster index.
@@ -91,11 +93,14 @@ __device__ __forceinline__ bool cam_generate_ray(const SppmLaunch& L, int st, in
 
 __global__ void __launch_bounds__(256) k_sppm_cam_generate(SppmLaunch L) {
     for (int st = L.range_begin + blockIdx.x * blockDim.x + threadIdx.x; st < L.range_end; st += gridDim.x * blockDim.x) {
-        int pix;
-        float3 o, d;
-        if (!cam_generate_ray(L, st, pix, o, d)) continue;
-        const int q = queue_claim(&L.counters[1]);
-        L.ro[0][q] = f4(o, TR_INF);
+        int pix = 0;
+        float3 o = f3s(0.0f), d = f3s(1.0f);
+        // no compaction at level 1: queue slot = path index (one same-address atomic per warp costs more than the few
+        // padding slots, which get a ray that cannot hit anything: t_max < 0)
+        const bool live = cam_generate_ray(L, st, pix, o, d);
+        const int q = st - L.range_begin;
+        if (st == L.range_end - 1) L.counters[1] = L.range_end - L.range_begin;
+        L.ro[0][q] = f4(o, live ? TR_INF : -1.0f);
         L.rd[0][q] = f4(d, __int_as_float(st));          // the path carries its STORAGE slot
         L.rw[0][q] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(pix));   // ... and its raster index (RNG key)
     }
@@ -164,7 +169,10 @@ __device__ __forceinline__ bool cam_shade_ray(const SppmLaunch& L, int level, fl
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_sppm_cam_shade(SppmLaunch L, int level) {
+#ifndef TR_SPPM_SHADE_MIN_BLOCKS
+#define TR_SPPM_SHADE_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, TR_SPPM_SHADE_MIN_BLOCKS) k_sppm_cam_shade(SppmLaunch L, int level) {
     const int cur = (level - 1) & 1, nxt = level & 1;
     const int n = min(L.counters[level], L.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -261,9 +269,21 @@ __global__ void __launch_bounds__(256) k_grid_bounds(SppmLaunch L) {
         }
         mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, off));
     }
-    if ((threadIdx.x & 31) == 0 && mr > 0.0f) {
-        for (int k = 0; k < 3; ++k) { atomic_min_float(&L.grid->lo[k], lo[k]); atomic_max_float(&L.grid->hi[k], hi[k]); }
-        atomic_max_float(&L.grid->max_radius, mr);
+    // one set of atomics per CTA, not per warp: all of them hit the same seven words (ncu: 48 us at 8 % issue utilisation
+    // for a 40 MB read - serialised same-address atomics)
+    __shared__ float s_red[8][7];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { for (int k = 0; k < 3; ++k) { s_red[w][k] = lo[k]; s_red[w][3 + k] = hi[k]; } s_red[w][6] = mr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 1; j < (int)(blockDim.x >> 5); ++j) {
+            for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], s_red[j][k]); hi[k] = fmaxf(hi[k], s_red[j][3 + k]); }
+            mr = fmaxf(mr, s_red[j][6]);
+        }
+        if (mr > 0.0f) {
+            for (int k = 0; k < 3; ++k) { atomic_min_float(&L.grid->lo[k], lo[k]); atomic_max_float(&L.grid->hi[k], hi[k]); }
+            atomic_max_float(&L.grid->max_radius, mr);
+        }
     }
 }
 
@@ -297,10 +317,15 @@ __device__ __forceinline__ bool to_grid(const GridParams& g, float3 p, int cell[
     }
     return in;
 }
-__device__ __forceinline__ unsigned int grid_hash(int x, int y, int z, unsigned int size) {    // sppm.jl:497-501, UInt64 math (Q10)
+// sppm.jl:497-501, UInt64 math (Q10).  Cell coordinates are < 2^30, so h < 2^57; with L = ceil(log2 size), k = 57 + L and
+// magic = ceil(2^k / size) (< 2^58 + 1), floor(h * magic / 2^k) == floor(h / size) exactly (error h * e / 2^k < 1 / size for
+// e < 1) - one 64x64 high multiply instead of the ~100-instruction 64-bit modulo that dominated k_grid_insert.
+__device__ __forceinline__ unsigned int grid_hash(int x, int y, int z, const SppmLaunch& L) {
     const unsigned long long h = ((unsigned long long)x * 73856093ull) ^ ((unsigned long long)y * 19349663ull) ^
                                  ((unsigned long long)z * 83492791ull);
-    return (unsigned int)(h % (unsigned long long)size);
+    if (L.hash_shift < 0) return (unsigned int)(h % (unsigned long long)(unsigned int)L.npix);
+    const unsigned long long q = __umul64hi(h, L.hash_magic) >> L.hash_shift;
+    return (unsigned int)(h - q * (unsigned long long)(unsigned int)L.npix);
 }
 
 template <bool FILL>
@@ -316,7 +341,7 @@ __global__ void __launch_bounds__(256) k_grid_insert(SppmLaunch L) {
         to_grid(g, f3(A.x - r, A.y - r, A.z - r), c0);
         to_grid(g, f3(A.x + r, A.y + r, A.z + r), c1);
         for (int z = c0[2]; z <= c1[2]; ++z) for (int y = c0[1]; y <= c1[1]; ++y) for (int x = c0[0]; x <= c1[0]; ++x) {
-            const unsigned int h = grid_hash(x, y, z, (unsigned int)L.npix);
+            const unsigned int h = grid_hash(x, y, z, L);
             // neighbouring pixels fall into the same cells (a cell holds thousands of visible points where the pixel
             // footprint is far below the radius): the lanes that hit the same cell right now issue ONE atomic
             const unsigned int active = __activemask();
@@ -409,10 +434,11 @@ __device__ __forceinline__ bool photon_generate_ray(const SppmLaunch& L, int j, 
 
 __global__ void __launch_bounds__(256) k_photon_generate(SppmLaunch L) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L.n_photons; j += gridDim.x * blockDim.x) {
-        float3 o, d, beta;
-        if (!photon_generate_ray(L, j, o, d, beta)) continue;
-        const int q = queue_claim(&L.counters[1]);
-        L.ro[0][q] = f4(o, TR_INF);
+        float3 o = f3s(0.0f), d = f3s(1.0f), beta = f3s(0.0f);
+        const bool live = photon_generate_ray(L, j, o, d, beta);
+        const int q = j;                                  // (see k_sppm_cam_generate)
+        if (j == L.n_photons - 1) L.counters[1] = L.n_photons;
+        L.ro[0][q] = f4(o, live ? TR_INF : -1.0f);
         L.rd[0][q] = f4(d, __int_as_float(j));
         L.rw[0][q] = f4(beta, luminance(beta));
     }
@@ -454,7 +480,7 @@ __device__ __forceinline__ bool photon_shade_ray(const SppmLaunch& L, int level,
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_photon_shade(SppmLaunch L, int level) {
+__global__ void __launch_bounds__(128, TR_SPPM_SHADE_MIN_BLOCKS) k_photon_shade(SppmLaunch L, int level) {
     const int cur = (level - 1) & 1, nxt = level & 1;
     const int n = min(L.counters[level], L.cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -531,7 +557,7 @@ __global__ void __launch_bounds__(128) k_photon_deposit(SppmLaunch L, int level)
         const float3 p = xyz(L.so[r]);
         int cell[3];
         if (!to_grid(g, p, cell)) continue;
-        const unsigned int hsh = grid_hash(cell[0], cell[1], cell[2], (unsigned int)L.npix);
+        const unsigned int hsh = grid_hash(cell[0], cell[1], cell[2], L);
         const unsigned int e0 = L.cell_start[hsh], e1 = L.cell_start[hsh + 1];
         if (e0 + sub * 32 >= e1) continue;
         const float3 wo = xyz(L.sd[r]), beta = xyz(L.sc_contrib[r]);
@@ -680,6 +706,17 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     ctx_device_camera(cam, &L.cam);
     if (ctx_device_film(c, film, &L.film, &s->table)) return 1;
     L.W = L.film.width; L.H = L.film.height; L.npix = L.W * L.H;
+    {   // grid_hash's division-free modulo
+        int lg = 0;
+        while ((1ull << lg) < (unsigned long long)L.npix) ++lg;
+        const int k = 57 + lg;
+        L.hash_shift = k - 64;
+        L.hash_magic = 0;
+        if (L.hash_shift >= 0) {
+            const unsigned __int128 one = (unsigned __int128)1 << k;
+            L.hash_magic = (unsigned long long)((one + (unsigned __int128)L.npix - 1) / (unsigned __int128)L.npix);
+        }
+    }
     if (c->rank < 0 || c->rank >= c->world) return c->fail("rank %d outside world %d", c->rank, c->world);
     L.world = c->world; L.rank = c->rank;
     L.chunk_rows = (L.H + L.world - 1) / L.world;
