@@ -120,6 +120,7 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "time_kernels")) c->time_kernels = v != 0;
     else if (!strcmp(key, "graph")) c->graph = v != 0;
     else if (!strcmp(key, "sppm_lanes")) { if (v < 0 || v > trace_ctx::MAX_LANES / 2) return c->fail("sppm_lanes must be in [0, 8]"); c->sppm_lanes = (int)v; }
+    else if (!strcmp(key, "sppm_pipeline")) { if (v < 1 || v > 8) return c->fail("sppm_pipeline must be in [1, 8]"); c->sppm_pipeline = (int)v; }
     else if (!strcmp(key, "deal")) c->deal = (int)v;
     else if (!strcmp(key, "rank")) { if (c->comm) return c->fail("rank is fixed by trace_comm_init"); c->rank = (int)v; }
     else if (!strcmp(key, "world")) { if (c->comm) return c->fail("world is fixed by trace_comm_init"); if (v < 1) return c->fail("world must be >= 1"); c->world = (int)v; }

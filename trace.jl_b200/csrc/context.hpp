@@ -87,6 +87,7 @@ struct trace_ctx {
     // not.  Keyed by every launch parameter; camera and seed live in a device block so they may change between replays
     int graph = 1;
     int sppm_lanes = 0;           // sub-ranges of each SPPM pass on concurrent streams (0: by scene size)
+    int sppm_pipeline = 2;        // SPPM iterations in flight (camera pass / photon tracing of it+1 overlap grid, deposits, collectives of it)
     int deal = -2;                // groups of tiles dealt round-robin to the batches: g > 0 tiles, -r: r tile rows, 0: contiguous bands
     cudaGraphExec_t wh_graph = nullptr;
     std::string wh_graph_key;

@@ -145,8 +145,9 @@ __device__ __forceinline__ bool cam_shade_ray(const SppmLaunch& L, int level, fl
     const bool is_diffuse = num_components(lobes, LB_DIFFUSE | LB_REFLECTION | LB_TRANSMISSION) > 0;
     const bool is_glossy = num_components(lobes, LB_GLOSSY | LB_REFLECTION | LB_TRANSMISSION) > 0;
     if (is_diffuse || (is_glossy && level == L.max_depth)) {
-        const float r = L.tau_r[slot].w;
-        L.vpA[slot] = f4(it.p, r * r);
+        // (the search radius is attached when the grid is built: the camera pass must not depend on the previous
+        // iteration's update, so that it can run ahead of it - see the pipeline in sppm_iteration_async)
+        L.vpA[slot] = f4(it.p, 0.0f);
         L.vpB[slot] = f4(wo, __uint_as_float(it.material));
         L.vpC[slot] = f4(fr.ns, is_black3(beta) ? 0.0f : 1.0f);
         L.vpD[slot] = f4(fr.ss, 0.0f);
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(256) k_grid_insert(SppmLaunch L) {
                 if (lane == leader) base = atomicAdd(&L.cell_cursor[h], n_peers);
                 base = __shfl_sync(peers, base, leader);
                 const unsigned int slot = base + (unsigned int)__popc(peers & ((1u << lane) - 1u));
-                if (slot < L.items_cap) { L.cell_items[slot] = (unsigned int)pix; L.cell_vp[slot] = make_float4(A.x, A.y, A.z, A.w); }
+                if (slot < L.items_cap) { L.cell_items[slot] = (unsigned int)pix; L.cell_vp[slot] = make_float4(A.x, A.y, A.z, r * r); }
             }
         }
     }
@@ -646,8 +647,20 @@ __global__ void k_sppm_stats(int* counters, unsigned long long* stats, int max_d
 // before their slowest ray (0.2-0.5 ms in the 88k-triangle glass block, whatever the ray count).  Photon TRACING does
 // not need the grid - only the deposits do - so it runs on its own streams concurrently with the camera pass, and each
 // pass is cut into `K` sub-ranges on separate streams whose latency-bound tails overlap.
+// Pipeline: the camera pass and the photon tracing of an iteration depend on nothing the previous iteration computes
+// (paths are functions of (seed, pixel, iteration) / the Halton index; the radius enters only when the grid is built), so
+// `D` iterations are in flight: iteration `it` uses slot (it - 1) % D - its own visible-point arrays, ray queues, request
+// queue and streams - and only the chain grid -> deposit -> (all-reduce) -> update is serial on the main stream.  The
+// latency-bound tails of one iteration's deep bounce levels (a traversal launch cannot end before its slowest ray) are
+// filled by the next iteration's wide launches, and with a communicator the collectives overlap the next camera pass.
+static const int SPPM_MAX_SLOTS = 8;
 struct SppmState {
-    SppmLaunch L;
+    SppmLaunch L;                   // slot 0's launch block (per-pixel state shared by all slots)
+    SppmLaunch slotL[SPPM_MAX_SLOTS];
+    int D = 1, cur_slot = 0;
+    bool pipelined = false;         // set while sppm_iteration_async drives the passes (the stepwise API stays on slot 0)
+    DevBuf vp_extra[SPPM_MAX_SLOTS][5];
+    cudaEvent_t ev_slot_free[SPPM_MAX_SLOTS] = {};     // recorded on the main stream after the update that releases the slot
     DevBuf pix[10], grid, cells[4], scan_sums, q[10], pq[10], table, lights;
     float r0;
     int photon_cap;                 // photons one lane can hold
@@ -663,6 +676,8 @@ void sppm_free(trace_ctx* c) {                 // releases the device memory too
     if (!c->sppm) return;
     SppmState* s = c->sppm;
     for (auto& b : s->pix) b.release();
+    for (auto& sl : s->vp_extra) for (auto& b : sl) b.release();
+    for (auto& e : s->ev_slot_free) if (e) cudaEventDestroy(e);
     for (auto& b : s->cells) b.release();
     for (auto& b : s->q) b.release();
     for (auto& b : s->pq) b.release();
@@ -749,6 +764,16 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     // costs every ray ~1000 node visits), not bound by a few slow rays (profiles/r1_experiments.md)
     const int K = c->sppm_lanes > 0 ? c->sppm_lanes : 1;
     s->Kc = s->Kp = std::min(K, trace_ctx::MAX_LANES / 2);
+    // iterations in flight (see SppmState): every slot needs Kc + Kp lanes (streams, counter blocks)
+    s->D = std::max(1, std::min(std::min(c->sppm_pipeline, SPPM_MAX_SLOTS), trace_ctx::MAX_LANES / (s->Kc + s->Kp)));
+    s->cur_slot = 0; s->pipelined = false;
+    for (int d = 0; d < s->D; ++d)
+        if (!s->ev_slot_free[d]) TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_slot_free[d], cudaEventDisableTiming));
+    for (int d = 1; d < s->D; ++d)
+        for (int k = 0; k < 5; ++k) {
+            TR_CUDA(c, s->vp_extra[d][k].ensure(f4b));
+            TR_CUDA(c, cudaMemsetAsync(s->vp_extra[d][k].p, 0, f4b, c->stream));
+        }
     if (!s->ev_ph_fork) TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_ph_fork, cudaEventDisableTiming));
     if (!s->ev_grid) TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_grid, cudaEventDisableTiming));
     // camera queues hold this rank's pixels, photon queues one chunk of photons; both are cut evenly over the lanes
@@ -761,12 +786,15 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     L.flags = ctx_icounters_lane(c, 0);
     L.stats = ctx_stats64(c);
     L.cap = 0; L.cap_shadow = 0; L.range_begin = L.range_end = 0;
+    // lanes of all slots: lane index = slot * K_ + sub-range
     auto carve = [&](DevBuf* q, int K_, size_t cap, std::vector<SppmLaunch>& lanes, int lane0) -> int {
         const size_t cap_sh = std::min<size_t>(cap * (size_t)max_depth, (size_t)1 << 30);
-        for (int k = 0; k < 7; ++k) TR_CUDA(c, q[k].ensure((size_t)K_ * cap * sizeof(float4)));
-        for (int k = 7; k < 10; ++k) TR_CUDA(c, q[k].ensure((size_t)K_ * cap_sh * sizeof(float4)));
-        lanes.assign((size_t)K_, L);
-        for (int l = 0; l < K_; ++l) {
+        const int n_lanes = s->D * K_;
+        for (int k = 0; k < 7; ++k) TR_CUDA(c, q[k].ensure((size_t)n_lanes * cap * sizeof(float4)));
+        for (int k = 7; k < 10; ++k) TR_CUDA(c, q[k].ensure((size_t)n_lanes * cap_sh * sizeof(float4)));
+        lanes.resize((size_t)n_lanes);
+        for (int l = 0; l < n_lanes; ++l) {
+            lanes[l] = s->slotL[l / K_];
             SppmLaunch& W = lanes[l];
             W.ro[0] = q[0].as<float4>() + l * cap; W.ro[1] = q[1].as<float4>() + l * cap;
             W.rd[0] = q[2].as<float4>() + l * cap; W.rd[1] = q[3].as<float4>() + l * cap;
@@ -801,15 +829,25 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     TR_CUDA(c, cudaMemcpyAsync(s->lights.p, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
     L.light_cdf = s->lights.as<float>(); L.light_func = s->lights.as<float>() + nl + 1; L.light_func_int = func_int;
-    if (carve(s->q, s->Kc, cam_cap, s->cam_lane, 0) || carve(s->pq, s->Kp, ph_cap, s->ph_lane, s->Kc)) return 1;
-    for (int l = 0; l < s->Kc; ++l) {
+    for (int d = 0; d < s->D; ++d) {
+        s->slotL[d] = L;
+        if (d > 0) {
+            SppmLaunch& S = s->slotL[d];
+            S.vpA = s->vp_extra[d][0].as<float4>(); S.vpB = s->vp_extra[d][1].as<float4>(); S.vpC = s->vp_extra[d][2].as<float4>();
+            S.vpD = s->vp_extra[d][3].as<float4>(); S.vpE = s->vp_extra[d][4].as<float4>();
+        }
+    }
+    if (carve(s->q, s->Kc, cam_cap, s->cam_lane, 0) || carve(s->pq, s->Kp, ph_cap, s->ph_lane, s->D * s->Kc)) return 1;
+    for (int l = 0; l < s->D * s->Kc; ++l) {
         const size_t s0 = (size_t)L.rank * rank_slots;
-        s->cam_lane[l].range_begin = (int)(s0 + std::min(rank_slots, (size_t)l * cam_cap));
-        s->cam_lane[l].range_end = (int)(s0 + std::min(rank_slots, (size_t)(l + 1) * cam_cap));
+        const int sub = l % s->Kc;
+        s->cam_lane[l].range_begin = (int)(s0 + std::min(rank_slots, (size_t)sub * cam_cap));
+        s->cam_lane[l].range_end = (int)(s0 + std::min(rank_slots, (size_t)(sub + 1) * cam_cap));
     }
     k_sppm_init<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L, r0);
     c->stats.kernel_launches++;
     TR_CUDA(c, cudaGetLastError());
+    for (int d = 0; d < s->D; ++d) TR_CUDA(c, cudaEventRecord(s->ev_slot_free[d], c->stream));      // every slot starts out free
     s->active = true;
     return 0;
 }
@@ -896,18 +934,18 @@ static int sppm_camera_pass_async(trace_ctx* c, int iteration) {
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_camera_pass: call trace_sppm_begin first");
     SppmState* s = c->sppm;
     s->L.iteration = iteration;
-    if (s->Kc == 1) {
-        LaneScope scope(c, 0, c->stream);
-        if (sppm_camera_lane(c, s, 0, iteration)) return 1;
-    } else {
-        TR_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
-        for (int l = 0; l < s->Kc; ++l) {
-            TR_CUDA(c, cudaStreamWaitEvent(c->side[l], c->ev_fork, 0));
-            LaneScope scope(c, l, c->side[l]);
-            if (sppm_camera_lane(c, s, l, iteration)) return 1;
-            TR_CUDA(c, cudaEventRecord(c->ev_join[l], c->side[l]));
-            TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[l], 0));
-        }
+    // the slot's lanes wait only until the update that last used the slot's visible-point arrays has run
+    // (D iterations back); the main stream then waits for them: everything after this call sees the visible points
+    const int slot = s->pipelined ? (iteration - 1) % s->D : 0;
+    s->cur_slot = slot;
+    s->slotL[slot].iteration = iteration;
+    for (int l = 0; l < s->Kc; ++l) {
+        const int lane = slot * s->Kc + l;
+        TR_CUDA(c, cudaStreamWaitEvent(c->side[lane], s->ev_slot_free[slot], 0));
+        LaneScope scope(c, lane, c->side[lane]);
+        if (sppm_camera_lane(c, s, lane, iteration)) return 1;
+        TR_CUDA(c, cudaEventRecord(c->ev_join[lane], c->side[lane]));
+        TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[lane], 0));
     }
     TR_CUDA(c, cudaGetLastError());
     return 0;
@@ -932,7 +970,7 @@ static int sppm_build_grid_async(trace_ctx* c) {
     cudaSetDevice(c->device);
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_build_grid: call trace_sppm_begin first");
     SppmState* s = c->sppm;
-    SppmLaunch& L = s->L;
+    SppmLaunch& L = s->slotL[s->cur_slot];
     const int g_stream = persistent_grid(c, 8);
     const int n_cells = L.npix + 1;
     const int scan_blocks = (n_cells + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
@@ -1030,13 +1068,17 @@ extern "C" int trace_sppm_trace_photons(trace_ctx* c, int iteration, int64_t beg
     s->traced_it = -1;
     if (end - begin > (int64_t)s->photon_cap * s->Kp) return 0;          // does not fit: photon_pass will chunk it
     const int64_t per = (end - begin + s->Kp - 1) / s->Kp;
-    TR_CUDA(c, cudaEventRecord(s->ev_ph_fork, c->stream));               // after the previous iteration's deposits / update
+    // Photon paths read nothing an earlier iteration writes; the lane's own stream orders them after the deposits that
+    // last read its request queue (D iterations back).  Only a session's first use of a lane waits for the main stream.
+    const int slot = s->pipelined ? (iteration - 1) % s->D : 0;
+    const bool first_use = iteration <= (s->pipelined ? s->D : 1);
+    if (first_use) TR_CUDA(c, cudaEventRecord(s->ev_ph_fork, c->stream));
     for (int j = 0; j < s->Kp; ++j) {
-        const int lane = s->Kc + j;
+        const int idx = slot * s->Kp + j, lane = s->D * s->Kc + idx;
         const int64_t b = std::min(end, begin + j * per), e = std::min(end, b + per);
-        TR_CUDA(c, cudaStreamWaitEvent(c->side[lane], s->ev_ph_fork, 0));
+        if (first_use) TR_CUDA(c, cudaStreamWaitEvent(c->side[lane], s->ev_ph_fork, 0));
         LaneScope scope(c, lane, c->side[lane]);
-        if (sppm_trace_lane(c, s, j, iteration, b, (int)(e - b))) return 1;
+        if (sppm_trace_lane(c, s, idx, iteration, b, (int)(e - b))) return 1;
     }
     TR_CUDA(c, cudaGetLastError());
     s->traced_it = iteration; s->traced_begin = begin; s->traced_end = end;
@@ -1058,11 +1100,12 @@ extern "C" int trace_sppm_photon_pass(trace_ctx* c, int iteration, int64_t begin
         s->traced_it = -1;
         // the deposits need the grid (main stream): every photon lane waits for it, deposits, and joins the main stream
         TR_CUDA(c, cudaEventRecord(s->ev_grid, c->stream));
+        const int slot = s->pipelined ? (iteration - 1) % s->D : 0;
         for (int j = 0; j < s->Kp; ++j) {
-            const int lane = s->Kc + j;
+            const int idx = slot * s->Kp + j, lane = s->D * s->Kc + idx;
             TR_CUDA(c, cudaStreamWaitEvent(c->side[lane], s->ev_grid, 0));
             LaneScope scope(c, lane, c->side[lane]);
-            if (sppm_deposit_lane(c, s, j)) return 1;
+            if (sppm_deposit_lane(c, s, idx)) return 1;
             TR_CUDA(c, cudaEventRecord(c->ev_join[lane], c->side[lane]));
             TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[lane], 0));
         }
@@ -1097,11 +1140,13 @@ extern "C" int trace_sppm_update(trace_ctx* c) {
     if (!c) return 1;
     cudaSetDevice(c->device);
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_update: call trace_sppm_begin first");
+    SppmState* s = c->sppm;
     c->kev_begin(TRACE_K_UPDATE);
-    k_sppm_update<<<persistent_grid(c, 4), 256, 0, c->stream>>>(c->sppm->L);
+    k_sppm_update<<<persistent_grid(c, 4), 256, 0, c->stream>>>(s->slotL[s->cur_slot]);
     c->kev_end();
     c->stats.kernel_launches++;
     TR_CUDA(c, cudaGetLastError());
+    TR_CUDA(c, cudaEventRecord(s->ev_slot_free[s->cur_slot], c->stream));     // the slot's visible-point arrays may be overwritten
     return 0;
 }
 
@@ -1143,12 +1188,14 @@ static int sppm_iteration_async(trace_ctx* c, int it) {
     const bool multi = c->comm != nullptr && c->world > 1;
     const int64_t P = L.photons_per_iteration;
     const int64_t b = multi ? P * c->rank / c->world : 0, e = multi ? P * (c->rank + 1) / c->world : P;
+    struct Flag { bool& f; explicit Flag(bool& f_) : f(f_) { f = true; } ~Flag() { f = false; } } pipelined(s->pipelined);
     // photon tracing first: it does not need the grid and overlaps the camera pass (and the all-gather) on its own stream
     if (trace_sppm_trace_photons(c, it, b, e) || sppm_camera_pass_async(c, it)) return 1;
     if (multi) {
         // rank r owns slice r of every per-pixel array (storage order): five in-place all-gathers of the visible points
         const size_t slice = (size_t)L.nstore / (size_t)c->world * 4;
-        float4* arr[5] = {L.vpA, L.vpB, L.vpC, L.vpD, L.vpE};
+        const SppmLaunch& S = s->slotL[s->cur_slot];
+        float4* arr[5] = {S.vpA, S.vpB, S.vpC, S.vpD, S.vpE};
         for (int k = 0; k < 5; ++k) {
             float* base = reinterpret_cast<float*>(arr[k]);
             if (comm_allgather(c, base + (size_t)c->rank * slice, base, slice)) return 1;
