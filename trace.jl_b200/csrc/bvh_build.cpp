@@ -19,6 +19,10 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#include <memory>
 #include <cstdlib>
 #include <condition_variable>
 #include <functional>
@@ -29,9 +33,20 @@
 
 #include "../../include/trace_cuda.h"
 
+// (a std::vector would zero-fill 640 MB single-threaded for the 10 M-triangle tree before the parallel stitch writes it)
+template <class T>
+struct RawArray {
+    std::unique_ptr<T[]> p;
+    size_t n = 0;
+    void resize(size_t m) { p.reset(new T[m]); n = m; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T* data() const { return p.get(); }
+    T& operator[](size_t i) const { return p[i]; }
+};
 struct trace_bvh {
-    std::vector<trace_bvh_node> nodes;
-    std::vector<uint32_t> order;
+    RawArray<trace_bvh_node> nodes;
+    RawArray<uint32_t> order;
 };
 
 namespace {
@@ -39,6 +54,17 @@ namespace {
 const float kInf = std::numeric_limits<float>::infinity();
 
 // Julia's min/max on floats: NaN propagates, -0.0 orders below +0.0.
+// Branch-free on x86 (the min / max passes are the build's inner loops): MINSS returns its SECOND operand when the two
+// compare equal or unordered, so min(a, b) | min(b, a) is the smaller value when they differ, -0.0 for a +-0 tie (sign
+// bits OR-ed) and a NaN when either is NaN (all-ones exponent, non-zero mantissa survive the OR); max(a, b) =
+// -min(-a, -b) (sign flips are exact).
+#if defined(__SSE2__)
+inline float fmin_jl(float a, float b) {
+    const __m128 x = _mm_set_ss(a), y = _mm_set_ss(b);
+    return _mm_cvtss_f32(_mm_or_ps(_mm_min_ss(x, y), _mm_min_ss(y, x)));
+}
+inline float fmax_jl(float a, float b) { return -fmin_jl(-a, -b); }
+#else
 inline float fmin_jl(float a, float b) {
     if (a != a || b != b) return a + b;
     if (b < a) return b;
@@ -51,6 +77,7 @@ inline float fmax_jl(float a, float b) {
     if (a == b && !std::signbit(b)) return b;
     return a;
 }
+#endif
 
 struct Box {
     float lo[3], hi[3];
@@ -141,34 +168,49 @@ int build_threads() {
 
 // Nodes with more primitives than this are split in the sequential "top" phase with their O(count) passes run in
 // parallel; smaller ones become independent subtree jobs for the thread pool.
-const int64_t kTopThreshold = 1 << 16;
+const int64_t kTopThreshold = 1 << 16;      // upper bound; build_tree lowers it for small inputs so that every thread gets jobs
 
 struct Split { bool leaf; int axis; int64_t mid; trace_bvh_node node; };
+
+// One primitive of the build: world bounds, centroid (bounds.jl: 0.5 lo + 0.5 hi) and its original index, 40 bytes.  The
+// build permutes these RECORDS, not an index array: every pass over a node's range then streams contiguous memory (a
+// subtree's working set is its own slice) instead of gathering 36 bytes per primitive from all over the input arrays -
+// the gathers were ~80 % of the build time at 10 M triangles.
+struct Rec { float b[6]; float c[3]; uint32_t id; };
 
 // ---- the reference's split of perm[from..to] (src/accel/bvh.jl:87-185; quirks Q16).  `threads` > 1 runs the reductions
 // and the bucket evaluation in parallel: min / max reductions are exact and order-independent, and the partition's
 // swaps (whose ORDER defines the resulting permutation) stay sequential, so the tree is bit-identical to the
 // one-threaded build.
+// bounds of the primitives and of their centroids over rec[from .. from + count)
+static void range_bounds(const Rec* rec, int64_t from, int64_t count, int parts, Box& all, Box& cb) {
+    if (parts == 1) {
+        all.reset(); cb.reset();
+        for (int64_t i = from; i < from + count; ++i) { all.grow(rec[i].b, rec[i].b + 3); cb.grow(rec[i].c, rec[i].c); }
+        return;
+    }
+    std::vector<Box> pa((size_t)parts), pc((size_t)parts);
+    parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
+        Box a, c; a.reset(); c.reset();
+        for (int64_t i = from + b; i < from + e; ++i) { a.grow(rec[i].b, rec[i].b + 3); c.grow(rec[i].c, rec[i].c); }
+        pa[(size_t)p] = a; pc[(size_t)p] = c;
+    });
+    all = pa[0]; cb = pc[0];
+    for (int p = 1; p < parts; ++p) { all.grow(pa[(size_t)p]); cb.grow(pc[(size_t)p]); }
+}
+
 struct LiteralSplitter {
-    const float* pb; const float* cen; uint32_t* perm; int max_prims;
-    std::vector<uint8_t>* pred;        // scratch of the top phase (n entries)
+    Rec* rec; int max_prims;
+    std::vector<uint8_t>* pred;        // scratch of the top phase (n entries each)
+    uint32_t* idx; Rec* tmp;
     static const int NB = 12;
 
     Split operator()(int64_t from, int64_t to, int threads) const {
         Split r; r.leaf = false; r.axis = 0; r.mid = from;
         const int64_t count = to - from + 1;
         const int parts = (threads > 1 && count >= 32768) ? threads : 1;
-        std::vector<Box> pa((size_t)parts), pc((size_t)parts);
-        parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
-            Box all, cb; all.reset(); cb.reset();
-            for (int64_t i = from + b; i < from + e; ++i) {
-                const float* bb = pb + 6 * (size_t)perm[i]; all.grow(bb, bb + 3);
-                const float* c = &cen[3 * (size_t)perm[i]]; cb.grow(c, c);
-            }
-            pa[(size_t)p] = all; pc[(size_t)p] = cb;
-        });
-        Box all = pa[0], cb = pc[0];
-        for (int p = 1; p < parts; ++p) { all.grow(pa[(size_t)p]); cb.grow(pc[(size_t)p]); }
+        Box all, cb;
+        range_bounds(rec, from, count, parts, all, cb);
         for (int k = 0; k < 3; ++k) { r.node.bmin[k] = all.lo[k]; r.node.bmax[k] = all.hi[k]; }
         if (count == 1) { r.leaf = true; return r; }
         const int axis = cb.widest();
@@ -177,30 +219,38 @@ struct LiteralSplitter {
         // relative position of a centroid along `axis`, bounds.jl:134-143 (offset)
         const bool any_extent = cb.hi[0] > cb.lo[0] || cb.hi[1] > cb.lo[1] || cb.hi[2] > cb.lo[2];
         const float extent = cb.hi[axis] > cb.lo[axis] ? cb.hi[axis] - cb.lo[axis] : 1.0f;
-        auto bucket = [&](uint32_t prim) -> int {
-            float o = cen[3 * (size_t)prim + axis] - cb.lo[axis];
+        auto bucket = [&](const Rec& pr) -> int {
+            float o = pr.c[axis] - cb.lo[axis];
             if (any_extent) o = o / extent;
             int b = (int)std::floor(12.0f * o);
             return b == NB ? NB - 1 : b;
         };
         if (count <= 2) {
             // partialsort!(view, 1, by = centroid[axis]) on two entries; mid = (from + to) ÷ 2 = from
-            if (cen[3 * (size_t)perm[to] + axis] < cen[3 * (size_t)perm[from] + axis]) std::swap(perm[from], perm[to]);
+            if (rec[to].c[axis] < rec[from].c[axis]) std::swap(rec[from], rec[to]);
             r.mid = (from + to) / 2;
             return r;
         }
-        std::vector<Box> pbk((size_t)parts * NB);
-        parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
-            Box* bk = &pbk[(size_t)p * NB];
-            for (int k = 0; k < NB; ++k) bk[k].reset();
-            for (int64_t i = from + b; i < from + e; ++i) {
-                const uint32_t pr = perm[i];
-                const float* bb = pb + 6 * (size_t)pr;
-                bk[bucket(pr)].grow(bb, bb + 3);
-            }
-        });
         Box bk[NB];
-        for (int k = 0; k < NB; ++k) { bk[k].point(0.0f); for (int p = 0; p < parts; ++p) bk[k].grow(pbk[(size_t)p * NB + k]); }
+        if (parts == 1) {
+            Box acc[NB];
+            for (int k = 0; k < NB; ++k) acc[k].reset();
+            for (int64_t i = from; i <= to; ++i) acc[bucket(rec[i])].grow(rec[i].b, rec[i].b + 3);
+            for (int k = 0; k < NB; ++k) { bk[k].point(0.0f); bk[k].grow(acc[k]); }
+        } else {
+            std::vector<Box> pbk((size_t)parts * NB);
+            uint8_t* bkt = pred->data();                              // the partition below reuses the bucket numbers
+            parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
+                Box* acc = &pbk[(size_t)p * NB];
+                for (int k = 0; k < NB; ++k) acc[k].reset();
+                for (int64_t i = from + b; i < from + e; ++i) {
+                    const int k = bucket(rec[i]);
+                    acc[k].grow(rec[i].b, rec[i].b + 3);
+                    bkt[i] = (uint8_t)k; idx[i] = (uint32_t)i;
+                }
+            });
+            for (int k = 0; k < NB; ++k) { bk[k].point(0.0f); for (int p = 0; p < parts; ++p) bk[k].grow(pbk[(size_t)p * NB + k]); }
+        }
         // prefix unions 0..i and suffix unions i..10 (bucket 11 never enters the right-hand side)
         Box pre[NB], suf[NB];
         pre[0] = bk[0];
@@ -227,14 +277,24 @@ struct LiteralSplitter {
         int64_t left = from;
         if (parts > 1) {
             uint8_t* pr = pred->data();
+            // The swaps' ORDER defines the permutation, so that loop stays sequential - but it runs on 4-byte positions
+            // (branch-free), and the 40-byte records are moved afterwards, in parallel.  `left != i` only ever skips
+            // i == from (left < i from then on).
+            for (int64_t i = from + 1; i <= to; ++i) {
+                const uint32_t p = (int)pr[i] <= best ? 1u : 0u, a = idx[i], b = idx[left];
+                idx[i] = p ? b : a;
+                idx[left] = p ? a : b;
+                left += p;
+            }
             parallel_chunks(count, parts, [&](int, int64_t b, int64_t e) {
-                for (int64_t i = from + b; i < from + e; ++i) pr[i] = bucket(perm[i]) <= best ? 1 : 0;     // (perm[i] is still untouched when the loop below reaches i)
+                for (int64_t i = from + b; i < from + e; ++i) tmp[i] = rec[idx[i]];
             });
-            for (int64_t i = from; i <= to; ++i)
-                if (left != i && pr[i]) { std::swap(perm[i], perm[left]); ++left; }
+            parallel_chunks(count, parts, [&](int, int64_t b, int64_t e) {
+                memcpy(rec + from + b, tmp + from + b, (size_t)(e - b) * sizeof(Rec));
+            });
         } else {
             for (int64_t i = from; i <= to; ++i)
-                if (left != i && bucket(perm[i]) <= best) { std::swap(perm[i], perm[left]); ++left; }
+                if (left != i && bucket(rec[i]) <= best) { std::swap(rec[i], rec[left]); ++left; }
         }
         r.mid = left;
         return r;
@@ -245,25 +305,17 @@ struct LiteralSplitter {
 // COUNT (cost = 1/8 + (nL*aL + nR*aR)/A), a node becomes a leaf when that is cheaper and it holds <=
 // max_node_primitives, the partition tests every element, and a degenerate split falls back to the median.
 struct SahSplitter {
-    const float* pb; const float* cen; uint32_t* perm; int max_prims;
+    Rec* rec; int max_prims;
     std::vector<uint8_t>* pred;
+    uint32_t* idx; Rec* tmp;
     static const int NB = 16;
 
     Split operator()(int64_t from, int64_t to, int threads) const {
         Split r; r.leaf = false; r.axis = 0;
         const int64_t count = to - from + 1;
         const int parts = (threads > 1 && count >= 32768) ? threads : 1;
-        std::vector<Box> pa((size_t)parts), pc((size_t)parts);
-        parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
-            Box all, cb; all.reset(); cb.reset();
-            for (int64_t i = from + b; i < from + e; ++i) {
-                const float* bb = pb + 6 * (size_t)perm[i]; all.grow(bb, bb + 3);
-                const float* c = &cen[3 * (size_t)perm[i]]; cb.grow(c, c);
-            }
-            pa[(size_t)p] = all; pc[(size_t)p] = cb;
-        });
-        Box all = pa[0], cb = pc[0];
-        for (int p = 1; p < parts; ++p) { all.grow(pa[(size_t)p]); cb.grow(pc[(size_t)p]); }
+        Box all, cb;
+        range_bounds(rec, from, count, parts, all, cb);
         for (int k = 0; k < 3; ++k) { r.node.bmin[k] = all.lo[k]; r.node.bmax[k] = all.hi[k]; }
         const int axis = cb.widest();
         r.axis = axis;
@@ -274,8 +326,8 @@ struct SahSplitter {
             bool split_done = false;
             if (cb.valid() && cb.hi[axis] > cb.lo[axis] && count >= 2) {
                 const float scale = (float)NB / (cb.hi[axis] - cb.lo[axis]);
-                auto bucket = [&](uint32_t prim) -> int {
-                    int b = (int)((cen[3 * (size_t)prim + axis] - cb.lo[axis]) * scale);
+                auto bucket = [&](const Rec& pr) -> int {
+                    int b = (int)((pr.c[axis] - cb.lo[axis]) * scale);
                     return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
                 };
                 std::vector<Box> pbk((size_t)parts * NB);
@@ -285,10 +337,8 @@ struct SahSplitter {
                     int64_t* cn = &pcnt[(size_t)p * NB];
                     for (int k = 0; k < NB; ++k) bk[k].reset();
                     for (int64_t i = from + b; i < from + e; ++i) {
-                        const uint32_t pr = perm[i];
-                        const float* bb = pb + 6 * (size_t)pr;
-                        const int k = bucket(pr);
-                        bk[k].grow(bb, bb + 3); cn[k]++;
+                        const int k = bucket(rec[i]);
+                        bk[k].grow(rec[i].b, rec[i].b + 3); cn[k]++;
                     }
                 });
                 Box bk[NB];
@@ -321,7 +371,7 @@ struct SahSplitter {
                 if (best >= 0 && (count > max_prims || best_cost < (float)count)) {
                     int64_t left = from;
                     for (int64_t i = from; i <= to; ++i)
-                        if (bucket(perm[i]) <= best) { std::swap(perm[i], perm[left]); ++left; }
+                        if (bucket(rec[i]) <= best) { std::swap(rec[i], rec[left]); ++left; }
                     mid = left - 1;
                     split_done = mid >= from && mid < to;
                 } else if (best >= 0 || count <= max_prims) {
@@ -331,9 +381,7 @@ struct SahSplitter {
             if (!leaf && !split_done) {
                 // median split along the axis (also: two primitives, or all centroids in one bucket)
                 mid = (from + to) / 2;
-                std::nth_element(perm + from, perm + mid, perm + to + 1, [&](uint32_t a, uint32_t b) {
-                    return cen[3 * (size_t)a + axis] < cen[3 * (size_t)b + axis];
-                });
+                std::nth_element(rec + from, rec + mid, rec + to + 1, [&](const Rec& a, const Rec& b) { return a.c[axis] < b.c[axis]; });
             }
         }
         r.leaf = leaf; r.mid = mid;
@@ -348,7 +396,7 @@ struct LocalTree { std::vector<trace_bvh_node> nodes; std::vector<uint32_t> orde
 // sequential build of perm[from..to] into `out` with LOCAL indices (node 0 = the subtree's root, order starts at 0), nodes
 // emitted in the flattened preorder (first child = parent + 1)
 template <class Splitter>
-int build_subtree(const Splitter& split, const uint32_t* perm, int64_t from, int64_t to, LocalTree& out) {
+int build_subtree(const Splitter& split, const Rec* rec, int64_t from, int64_t to, LocalTree& out) {
     std::vector<Task> todo;
     todo.push_back({from, to, -1});
     const int64_t node_limit = 8 * (to - from + 1) + 1024;     // a guard, never reached by terminating inputs
@@ -363,7 +411,7 @@ int build_subtree(const Splitter& split, const uint32_t* perm, int64_t from, int
         if (s.leaf) {
             s.node.offset = (uint32_t)out.order.size();
             s.node.meta = TRACE_NODE_LEAF | (uint32_t)(count < 0 ? 0 : count);
-            for (int64_t i = t.from; i <= t.to; ++i) out.order.push_back(perm[i]);
+            for (int64_t i = t.from; i <= t.to; ++i) out.order.push_back(rec[i].id);
             out.nodes.push_back(s.node);
         } else {
             s.node.offset = 0;
@@ -383,10 +431,12 @@ int build_subtree(const Splitter& split, const uint32_t* perm, int64_t from, int
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 template <class Splitter>
-int build_tree(Splitter split, uint32_t* perm, int64_t n, trace_bvh* bvh) {
+int build_tree(Splitter split, const Rec* rec, int64_t n, trace_bvh* bvh) {
     const int threads = build_threads();
     const bool prof = getenv("TRACE_BVH_PROFILE") != nullptr;
     const double t_begin = now_s();
+    // ~16 jobs per thread (subtree sizes vary a lot: the literal tree is unbalanced), never below 4096 primitives
+    const int64_t job_threshold = std::max<int64_t>(4096, std::min<int64_t>(kTopThreshold, n / (16 * (int64_t)threads)));
     struct Item { int kind; trace_bvh_node node; int64_t from, to; int64_t second_item; int job; };   // kind 0 interior, 1 leaf, 2 job
     std::vector<Item> items;
     std::vector<std::pair<int64_t, int64_t>> jobs;
@@ -399,7 +449,7 @@ int build_tree(Splitter split, uint32_t* perm, int64_t n, trace_bvh* bvh) {
         const int64_t me = (int64_t)items.size();
         if (t.patch_item >= 0) items[(size_t)t.patch_item].second_item = me;
         const int64_t count = t.to - t.from + 1;
-        if (threads == 1 ? false : count <= kTopThreshold) {
+        if (threads == 1 ? false : count <= job_threshold) {
             items.push_back({2, trace_bvh_node(), t.from, t.to, -1, (int)jobs.size()});
             jobs.push_back({t.from, t.to});
             continue;
@@ -432,7 +482,7 @@ int build_tree(Splitter split, uint32_t* perm, int64_t n, trace_bvh* bvh) {
                 const int64_t cnt = jobs[j].second - jobs[j].first + 1;
                 local[j].nodes.reserve((size_t)(2 * cnt + 16));
                 local[j].order.reserve((size_t)cnt);
-                rcs[j] = build_subtree(split, perm, jobs[j].first, jobs[j].second, local[j]);
+                rcs[j] = build_subtree(split, rec, jobs[j].first, jobs[j].second, local[j]);
             }
         };
         const int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, jobs.size()));
@@ -464,7 +514,7 @@ int build_tree(Splitter split, uint32_t* perm, int64_t n, trace_bvh* bvh) {
                 trace_bvh_node nd = it.node;
                 nd.offset = (uint32_t)order_base[(size_t)i];
                 bvh->nodes[(size_t)node_base[(size_t)i]] = nd;
-                for (int64_t k = it.from; k <= it.to; ++k) bvh->order[(size_t)(order_base[(size_t)i] + k - it.from)] = perm[k];
+                for (int64_t k = it.from; k <= it.to; ++k) bvh->order[(size_t)(order_base[(size_t)i] + k - it.from)] = rec[k].id;
             } else {
                 const LocalTree& lt = local[(size_t)it.job];
                 const uint32_t nb = (uint32_t)node_base[(size_t)i], ob = (uint32_t)order_base[(size_t)i];
@@ -491,17 +541,21 @@ int build_entry(const float* pb, int64_t n, int max_prims, trace_bvh** out) {
     if (!bvh) return 2;
     if (n == 0) { *out = bvh; return 0; }
     try {
-        std::vector<float> cen((size_t)n * 3);
-        std::vector<uint32_t> perm((size_t)n);
+        std::unique_ptr<Rec[]> rec(new Rec[(size_t)n]);          // (no value-initialisation pass: filled in parallel below)
         std::vector<uint8_t> pred((size_t)n);
+        const bool top_phase = build_threads() > 1 && n > 4096;      // scratch of the parallel partition
+        std::unique_ptr<uint32_t[]> idx(top_phase ? new uint32_t[(size_t)n] : nullptr);
+        std::unique_ptr<Rec[]> tmp(top_phase ? new Rec[(size_t)n] : nullptr);
         parallel_chunks(n, build_threads(), [&](int, int64_t b, int64_t e) {
             for (int64_t i = b; i < e; ++i) {
-                perm[(size_t)i] = (uint32_t)i;
-                for (int k = 0; k < 3; ++k) cen[3 * (size_t)i + k] = 0.5f * pb[6 * i + k] + 0.5f * pb[6 * i + 3 + k];
+                Rec& r = rec[(size_t)i];
+                r.id = (uint32_t)i;
+                for (int k = 0; k < 6; ++k) r.b[k] = pb[6 * i + k];
+                for (int k = 0; k < 3; ++k) r.c[k] = 0.5f * pb[6 * i + k] + 0.5f * pb[6 * i + 3 + k];
             }
         });
-        Splitter split{pb, cen.data(), perm.data(), max_prims, &pred};
-        const int rc = build_tree(split, perm.data(), n, bvh);
+        Splitter split{rec.get(), max_prims, &pred, idx.get(), tmp.get()};
+        const int rc = build_tree(split, rec.get(), n, bvh);
         if (rc) { delete bvh; return rc; }
     } catch (...) { delete bvh; return 2; }
     *out = bvh;

@@ -29,6 +29,8 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::string error;
 };
@@ -55,6 +57,8 @@ NcclApi* nccl_api() {
     api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
     api.ReduceScatter = (decltype(api.ReduceScatter))sym("ncclReduceScatter");
     api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     if (!ok) { dlclose(api.handle); api.handle = nullptr; }
     return &api;
@@ -148,5 +152,17 @@ int comm_allgather(trace_ctx* c, const float* send, float* recv, size_t send_cou
     NcclApi* a = nccl_api();
     if (!c->comm) return c->fail("no communicator: call trace_comm_init first");
     TR_NCCL(c, a->AllGather(send, recv, send_count, ncclFloat, (ncclComm_t)c->comm, c->stream));
+    return 0;
+}
+// several collectives of one exchange step fused into one NCCL launch (the five visible-point arrays of an SPPM iteration)
+int comm_group_begin(trace_ctx* c) {
+    NcclApi* a = nccl_api();
+    if (!c->comm) return c->fail("no communicator: call trace_comm_init first");
+    TR_NCCL(c, a->GroupStart());
+    return 0;
+}
+int comm_group_end(trace_ctx* c) {
+    NcclApi* a = nccl_api();
+    TR_NCCL(c, a->GroupEnd());
     return 0;
 }

@@ -87,7 +87,7 @@ struct trace_ctx {
     // not.  Keyed by every launch parameter; camera and seed live in a device block so they may change between replays
     int graph = 1;
     int sppm_lanes = 0;           // sub-ranges of each SPPM pass on concurrent streams (0: by scene size)
-    int sppm_pipeline = 2;        // SPPM iterations in flight (camera pass / photon tracing of it+1 overlap grid, deposits, collectives of it)
+    int sppm_pipeline = 4;        // SPPM iterations in flight (camera pass / photon tracing of it+1 overlap grid, deposits, collectives of it)
     int deal = -2;                // groups of tiles dealt round-robin to the batches: g > 0 tiles, -r: r tile rows, 0: contiguous bands
     cudaGraphExec_t wh_graph = nullptr;
     std::string wh_graph_key;
@@ -248,6 +248,8 @@ int comm_reduce_sum(trace_ctx* ctx, const float* send, float* recv, size_t count
 int comm_reduce_scatter_sum(trace_ctx* ctx, const float* send, float* recv, size_t recv_count);
 int comm_allreduce_sum(trace_ctx* ctx, float* buf, size_t count);
 int comm_allgather(trace_ctx* ctx, const float* send, float* recv, size_t send_count);
+int comm_group_begin(trace_ctx* ctx);
+int comm_group_end(trace_ctx* ctx);
 // implemented in whitted.cu / sppm.cu
 int whitted_render_device(trace_ctx* ctx, const trace_camera* cam, const trace_film_desc* film, int spp, int max_depth,
                           uint64_t seed, float* film_xyzw_device);
