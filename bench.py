@@ -260,6 +260,7 @@ class Env:
         import trace_jl_b200 as T
         from trace_jl_b200 import distributed as D
         self.torch, self.dist, self.T, self.D, self.args = torch, dist, T, D, args
+        self.t_start = time.perf_counter()
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -268,7 +269,9 @@ class Env:
         torch.cuda.set_device(self.local)
         self.dev = f"cuda:{self.local}"
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=torch.device(self.dev))
+            import datetime
+            # (a rank that dies must not leave the others waiting in a barrier for NCCL's default 10 minutes)
+            dist.init_process_group("nccl", device_id=torch.device(self.dev), timeout=datetime.timedelta(seconds=240))
         # one non-default stream for everything: the library's launches (and its NCCL collectives) and the CUDA events
         # below share it (torch's default stream has handle 0, which the library takes as "make your own")
         self.stream = torch.cuda.Stream(device=self.local)
@@ -279,6 +282,11 @@ class Env:
             self.ctx.set_option(k, getattr(args, k))
         if args.batch:
             self.ctx.set_option("batch", args.batch)
+
+    def note(self, msg):
+        """progress line on stderr (TRACE_BENCH_VERBOSE=1): which stage a rank reached, for post-mortems of multi-rank runs"""
+        if os.environ.get("TRACE_BENCH_VERBOSE"):
+            print(f"[bench rank {self.rank} +{time.perf_counter() - self.t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
     def barrier(self):
         if self.world > 1:
@@ -493,9 +501,11 @@ def bench_sppm(env, workload, steps, warmup, cpu_baseline=True):
     h, w = camera.film.pixels.shape[:2]
     cam_pod, fd = camera.pod(), camera.film.desc()
     ctx.set_option("time_kernels", 0)
+    env.note(f"{workload}: scene uploaded")
     sess = D.SPPMSession(ctx, scene, camera, p["r0"], p["max_depth"], p["photons"], 0x5EED0001)
     sess.step(max(3, warmup))
     env.barrier()
+    env.note(f"{workload}: warm-up done")
     ctx.reset_stats()
     sampler = ClockSampler(env.local)
     if rank == 0:
@@ -505,6 +515,7 @@ def bench_sppm(env, workload, steps, warmup, cpu_baseline=True):
     st = ctx.stats()
     launches = sum(env.sum_over_ranks([st["kernel_launches"]]))
     value = steps / (ms * 1e-3)
+    env.note(f"{workload}: timed iterations done ({value:.0f} it/s)")
     # serial pass with per-class CUDA events + counters: which kernel class dominates, and its algorithmic bytes
     ctx.set_option("time_kernels", 1)
     sess.step(1)
@@ -516,9 +527,14 @@ def bench_sppm(env, workload, steps, warmup, cpu_baseline=True):
     s1 = ctx.stats()
     ctx.set_option("time_kernels", 0)
     sess.close()
+    env.note(f"{workload}: per-class timing pass done")
     kk = kinds(s1)
-    timed_total = sum(v[0] for v in kk.values()) or 1e-9
-    share = {k: v[0] / timed_total for k, v in kk.items() if v[1]}
+    # the dominant class decides which extra passes (with collectives) follow: every rank must pick the SAME one, so the
+    # choice is made on the class times summed over the ranks, not on this rank's own
+    names = sorted(kk)
+    summed = dict(zip(names, env.sum_over_ranks([kk[k][0] for k in names])))
+    timed_total = sum(summed.values()) or 1e-9
+    share = {k: summed[k] / timed_total for k in names if kk[k][1]}
     dom = max(share, key=share.get)
     peak, peak_kind = load_peaks()
     rays = s1["rays_extend"] + s1["rays_shadow"]
@@ -532,6 +548,7 @@ def bench_sppm(env, workload, steps, warmup, cpu_baseline=True):
         sc = ctx.stats()
         s2.close()
         ctx.set_option("count_nodes", 0)
+        env.note(f"{workload}: counting pass done")
         n_cnt = max(1, sc["rays_extend"] + sc["rays_shadow"])
         npr, ppr = sc["nodes_visited"] / n_cnt, sc["prims_tested"] / n_cnt
         per_unit = 48.0 + 32.0 * npr + 48.0 * ppr
@@ -580,9 +597,11 @@ def bench_sppm(env, workload, steps, warmup, cpu_baseline=True):
                                             C.c_uint64(0x5EED0001 + i), C.cast(None, T._lib.SPPM_CB), None, C.c_void_p(rgb.data_ptr())))
 
     render(0)
+    env.note(f"{workload}: first e2e render done")
     n_renders = 3
     ms_e, wall_e = env.timed(lambda i: render(1 + i), n_renders)
     e2e_ms = max(ms_e, wall_e)
+    env.note(f"{workload}: e2e renders done")
     e2e = {"value": n_renders * n_it / (e2e_ms * 1e-3), "unit": "it/s",
            "h2d_bytes_per_step": int(world * (C.sizeof(cam_pod) + C.sizeof(fd)) / n_it), "d2h_bytes_per_step": int(world * h * w * 3 * 4 / n_it),
            "ms_per_step": e2e_ms / (n_renders * n_it),

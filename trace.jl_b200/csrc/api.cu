@@ -274,7 +274,7 @@ extern "C" int trace_scene_upload(trace_ctx* c, const trace_scene_desc* d) {
                 float4 a = nodes[2 * kids[k]], b = nodes[2 * kids[k] + 1];
                 if ((ch.meta >> 30) == 3 && (ch.meta & 0x3FFFFFFFu) == 0u) { a.x = a.y = a.z = a.w = qnan; b.x = b.y = qnan; }
                 const uint32_t ref = child_ref(kids[k]);
-                const uint32_t extra = k == 0 ? (n.meta >> 30) : 0u;          // split axis of THIS node, in the first half
+                const uint32_t extra = k == 0 ? (1u << (n.meta >> 30)) : 0u;  // split axis of THIS node as a bit (1 << axis), in the first half
                 memcpy(&b.z, &ref, 4); memcpy(&b.w, &extra, 4);
                 q[2 * k] = a; q[2 * k + 1] = b;
             }

@@ -19,6 +19,10 @@ struct RayPrep {            // quantities that depend on the ray only
     float mx, my, mz;       // SLAB 2: per-axis slack of the conservative interval, in units of t
     float mmax;             // max(mx, my, mz)
     bool any_zero;          // a direction component is 0: 1/d is Inf, slab products may be NaN - no shortcuts for this ray
+    // thresholds of slab_child_fast; +Inf for an any_zero ray, which makes both of its verdicts false (-> full test)
+    float fast_reject;      // 2 * mmax
+    float fast_behind;      // mmax
+    float fast_accept;      // 0
 };
 
 // Spatial slack of the conservative box test (SLAB 2), relative to the largest coordinate in play: 2^-17 ~ 7.6e-6,
@@ -53,6 +57,9 @@ __device__ __forceinline__ RayPrep prepare_ray(float3 o, float3 d, float scene_s
     r.mx = slack * fabsf(r.inv.x); r.my = slack * fabsf(r.inv.y); r.mz = slack * fabsf(r.inv.z);
     r.mmax = fmaxf(r.mx, fmaxf(r.my, r.mz));
     r.any_zero = (d.x == 0.0f) | (d.y == 0.0f) | (d.z == 0.0f);
+    r.fast_reject = r.any_zero ? TR_INF : 2.0f * r.mmax;
+    r.fast_behind = r.any_zero ? TR_INF : r.mmax;
+    r.fast_accept = r.any_zero ? TR_INF : 0.0f;
     return r;
 }
 
@@ -335,17 +342,18 @@ __device__ __forceinline__ bool slab_child(const float4 n0, const float4 n1, con
 //     spheres, where the guard is off).
 //   * otherwise UNDECIDED (grazing within the slack band, NaN boxes): the caller evaluates slab_child<2> in full.
 // About 26 instructions per child instead of 44; the undecided band is a few rays in a million box tests.
+// The kernels are bound by the ALU pipe (ncu: 68 % against 22 % on the FMA pipe), so this form avoids what it can there:
+// no selects by the direction's sign (1/d < 0 swaps the two products of an axis, so entry = min, exit = max of the pair -
+// the same six numbers, hence the same t_enter bits), and the any_zero exclusion is folded into per-ray thresholds
+// instead of being re-derived from the direction every iteration (predicates do not survive the loop).
 __device__ __forceinline__ void slab_child_fast(const float4 n0, const float4 n1, const RayPrep& r, float& t_enter_out, bool& accept, bool& reject) {
-    const float ax0 = ((r.nx ? n0.w : n0.x) - r.o.x) * r.inv.x;
-    const float ax1 = ((r.nx ? n0.x : n0.w) - r.o.x) * r.inv.x;
-    const float ay0 = ((r.ny ? n1.x : n0.y) - r.o.y) * r.inv.y;
-    const float ay1 = ((r.ny ? n0.y : n1.x) - r.o.y) * r.inv.y;
-    const float az0 = ((r.nz ? n1.y : n0.z) - r.o.z) * r.inv.z;
-    const float az1 = ((r.nz ? n0.z : n1.y) - r.o.z) * r.inv.z;
-    const float t_enter = fmaxf(fmaxf(ax0, ay0), az0);
-    const float t_exit = fminf(fminf(ax1, ay1), az1);
-    accept = (t_enter <= t_exit) & (t_exit > 0.0f);
-    reject = (((t_enter - t_exit) > 2.0f * r.mmax) | (t_exit < -r.mmax)) & ((__float_as_uint(n1.z) & TR_REF_SPHERE_BELOW) == 0u);
+    const float x0 = (n0.x - r.o.x) * r.inv.x, x1 = (n0.w - r.o.x) * r.inv.x;
+    const float y0 = (n0.y - r.o.y) * r.inv.y, y1 = (n1.x - r.o.y) * r.inv.y;
+    const float z0 = (n0.z - r.o.z) * r.inv.z, z1 = (n1.y - r.o.z) * r.inv.z;
+    const float t_enter = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+    const float t_exit = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    accept = (t_enter <= t_exit) & (t_exit > r.fast_accept);
+    reject = (((t_enter - t_exit) > r.fast_reject) | (t_exit < -r.fast_behind)) & ((__float_as_uint(n1.z) & TR_REF_SPHERE_BELOW) == 0u);
     t_enter_out = t_enter;
 }
 
@@ -357,7 +365,7 @@ __device__ __forceinline__ void slab_children(const float4 q0, const float4 q1, 
         bool a0, r0, a1, r1;
         slab_child_fast(q0, q1, r, t0, a0, r0);
         slab_child_fast(q2, q3, r, t1, a1, r1);
-        if (!r.any_zero & (a0 | r0) & (a1 | r1)) { s0 = a0; s1 = a1; return; }
+        if ((a0 | r0) & (a1 | r1)) { s0 = a0; s1 = a1; return; }
     }
     s0 = slab_child<SLAB>(q0, q1, r, t0);
     s1 = slab_child<SLAB>(q2, q3, r, t1);
@@ -381,7 +389,8 @@ __device__ __forceinline__ bool traverse_pair(const DeviceScene& sc, float3 o, f
     uint2 stack[TR_STACK_SIZE];
     uint2 tos = make_uint2(0u, 0u);
     int sp = 0;
-    const unsigned signs = (r.nx ? 1u : 0u) | (r.ny ? 2u : 0u) | (r.nz ? 4u : 0u);
+    unsigned signs = (r.nx ? 1u : 0u) | (r.ny ? 2u : 0u) | (r.nz ? 4u : 0u);
+    asm volatile("" : "+r"(signs));       // keep it in a register: ptxas otherwise re-derives it from d every iteration (7 ALU instructions)
     const bool cull_far = sc.n_spheres == 0;
     for (;;) {
         if (item & TR_REF_LEAF) {
@@ -418,7 +427,7 @@ __device__ __forceinline__ bool traverse_pair(const DeviceScene& sc, float3 o, f
             float t0, t1;
             bool s0, s1;
             slab_children<SLAB>(q0, q1, q2, q3, r, s0, s1, t0, t1);
-            const bool neg = (signs >> (__float_as_uint(q1.w) & 3u)) & 1u;      // near child = second child iff d[axis] < 0
+            const bool neg = (signs & __float_as_uint(q1.w)) != 0u;      // near child = second child iff d[axis] < 0 (q1.w = 1 << axis)
             const uint32_t ref0 = __float_as_uint(q1.z), ref1 = __float_as_uint(q3.z);
             const float near_t = neg ? t1 : t0, far_t = neg ? t0 : t1;
             const bool near_hit = (neg ? s1 : s0) & (near_t < tmax);               // tested now, as the reference does
