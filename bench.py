@@ -280,6 +280,9 @@ class Env:
         D.init_comm(self.ctx, self.rank, self.world)          # the library's own communicator (trace_comm_init)
         for k in ("slab", "walk", "lanes", "graph"):
             self.ctx.set_option(k, getattr(args, k))
+        for kv in (args.option or []):                     # experiments: any trace_set_option key=value
+            k, v = kv.split("=")
+            self.ctx.set_option(k, int(v))
         if args.batch:
             self.ctx.set_option("batch", args.batch)
 
@@ -671,6 +674,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="replay the Whitted render as one CUDA graph (0: direct launches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sppm", action="store_true")
+    ap.add_argument("--option", action="append", help="extra trace_set_option key=value (experiments), repeatable")
     ap.add_argument("--no-optin", action="store_true", help="skip the extra measurement on the opt-in SAH tree")
     ap.add_argument("--sppm-workloads", default="sppm-shadows-1024,sppm-caustic-moving,sppm-caustic-glass-d8",
                     help="SPPM sub-lines carried by the default Whitted line")

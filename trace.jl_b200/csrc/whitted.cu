@@ -661,7 +661,12 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
         TrRange nvtx_sum("whitted.film sum (NCCL)");
         float* rgbw = reinterpret_cast<float*>(L.film_rgbw);
         const float4* merged = L.film_rgbw;
-        if (c->film_mode == 0) { if (comm_reduce_sum(c, rgbw, rgbw, npix * 4, 0)) return 1; }
+        if (c->film_mode == 0) {
+            // whole film onto rank 0: ncclReduce, or (option film_sum 1) ncclAllReduce - on NVSwitch boxes NCCL can reduce
+            // inside the switch (NVLS), which beats the 8-rank reduce ring / tree for a 33 MB film
+            if (c->film_sum == 1) { if (comm_allreduce_sum(c, rgbw, npix * 4)) return 1; }
+            else if (comm_reduce_sum(c, rgbw, rgbw, npix * 4, 0)) return 1;
+        }
         else {
             const size_t chunk = (npix + (size_t)c->world - 1) / (size_t)c->world;
             if (comm_reduce_scatter_sum(c, rgbw, rgbw + (size_t)c->rank * chunk * 4, chunk * 4)) return 1;     // in place
