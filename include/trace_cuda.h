@@ -120,7 +120,8 @@ typedef struct trace_film_desc {
 /* kernel classes of the per-class timing in trace_stats */
 enum { TRACE_K_EXTEND = 0, TRACE_K_SHADOW = 1, TRACE_K_GENERATE = 2, TRACE_K_SHADE = 3, TRACE_K_SPLAT = 4,
        TRACE_K_GRID = 5 /* SPPM hash grid: bounds, count, scan, fill */, TRACE_K_DEPOSIT = 6, TRACE_K_UPDATE = 7,
-       TRACE_K_COUNT = 8 };
+       TRACE_K_COMM = 8 /* the library's NCCL collectives (film sum; visible-point all-gather, flux all-reduce) */,
+       TRACE_K_COUNT = 9 };
 typedef struct trace_stats {
     uint64_t rays_extend;        /* rays through closest-hit traversal */
     uint64_t rays_shadow;        /* rays through any-hit traversal */

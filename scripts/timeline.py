@@ -29,4 +29,4 @@ by_lane = {}
 for lane, kind, a, b in rows:
     by_lane.setdefault(int(lane), []).append((int(kind), float(a), float(b)))
 for lane in sorted(by_lane):
-    print(f"lane {lane:2d}: " + "  ".join(f"{'ESGHPRDU'[k]}[{a:5.2f},{b:5.2f}]" for k, a, b in by_lane[lane]))
+    print(f"lane {lane:2d}: " + "  ".join(f"{'ESGHPRDUC'[k]}[{a:5.2f},{b:5.2f}]" for k, a, b in by_lane[lane]))

@@ -33,7 +33,7 @@ def test_struct_layouts(T):
     assert C.sizeof(tl.FilmDesc) == 16 + 8 + 1024 + 4
     assert C.sizeof(tl.Camera) == 64 + 64 + 16
     assert C.sizeof(tl.SceneDesc) == 14 * 8
-    assert C.sizeof(tl.Stats) == 33 * 8      # 12 scalars + 2 x 8 per-class + 5 counters (include/trace_cuda.h trace_stats)
+    assert C.sizeof(tl.Stats) == 35 * 8      # 12 scalars + 2 x 9 per-class + 5 counters (include/trace_cuda.h trace_stats)
 
 
 def test_create_fails_loudly_without_gpu(T):

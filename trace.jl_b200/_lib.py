@@ -53,7 +53,7 @@ class Stats(C.Structure):
                 ("prims_tested", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_extend", C.c_double),
                 ("ms_shadow", C.c_double), ("ms_total", C.c_double), ("queue_overflows", C.c_uint64),
                 ("sppm_deposits", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
-                ("ms_kind", C.c_double * 8), ("launches_kind", C.c_uint64 * 8), ("sppm_candidates", C.c_uint64),
+                ("ms_kind", C.c_double * 9), ("launches_kind", C.c_uint64 * 9), ("sppm_candidates", C.c_uint64),
                 ("sppm_requests", C.c_uint64), ("sppm_grid_items", C.c_uint64), ("primary_rays", C.c_uint64),
                 ("primary_hits", C.c_uint64)]
 
@@ -62,7 +62,7 @@ class Stats(C.Structure):
 
 
 K_EXTEND, K_SHADOW, K_GENERATE, K_SHADE, K_SPLAT, K_GRID, K_DEPOSIT, K_UPDATE = range(8)
-KIND_NAMES = ["extend", "shadow", "generate", "shade", "splat", "grid", "deposit", "update"]
+KIND_NAMES = ["extend", "shadow", "generate", "shade", "splat", "grid", "deposit", "update", "comm"]
 
 
 SPPM_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float))

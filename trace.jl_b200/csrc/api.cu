@@ -111,7 +111,7 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "count_nodes")) c->count_nodes = v != 0;
     else if (!strcmp(key, "persist")) { if (v != 0) return c->fail("persist: the dynamic-ray-fetch kernels were measured slower in both rounds and removed (profiles/r2_experiments.md)"); }
     else if (!strcmp(key, "film_mode")) { if (v != 0 && v != 1) return c->fail("film_mode must be 0 (whole film on rank 0) or 1 (one band per rank)"); c->film_mode = (int)v; }
-    else if (!strcmp(key, "film_sum")) { if (v != 0 && v != 1) return c->fail("film_sum must be 0 (ncclReduce) or 1 (ncclAllReduce)"); c->film_sum = (int)v; }
+    else if (!strcmp(key, "film_sum")) { if (v < 0 || v > 2) return c->fail("film_sum must be 0 (ncclReduce), 1 (ncclAllReduce) or 2 (reduce-scatter + gather)"); c->film_sum = (int)v; }
     else if (!strcmp(key, "sppm_path")) { if (v < 0 || v > TR_MAX_DEPTH) return c->fail("sppm_path must be in [0, %d]", TR_MAX_DEPTH); c->sppm_path = (int)v; }
     else if (!strcmp(key, "fuse_primary")) c->fuse_primary = v != 0;
     else if (!strcmp(key, "walk")) { if (v != 0 && v != 1) return c->fail("walk must be 0 (one node per step, the reference loop) or 1 (pair nodes)"); c->leaf_wait = v ? TR_WALK_PAIR : 0; }

@@ -29,6 +29,8 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -57,6 +59,8 @@ NcclApi* nccl_api() {
     api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
     api.ReduceScatter = (decltype(api.ReduceScatter))sym("ncclReduceScatter");
     api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
     api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
     api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
@@ -164,5 +168,24 @@ int comm_group_begin(trace_ctx* c) {
 int comm_group_end(trace_ctx* c) {
     NcclApi* a = nccl_api();
     TR_NCCL(c, a->GroupEnd());
+    return 0;
+}
+// Sum of the ranks' buffers delivered to `root` as reduce-scatter (every link busy, each rank sums 1/world of the
+// buffer) + a gather of the summed chunks onto the root (grouped send / recv): for a 33 MB film on 8 GPUs ~0.1 ms
+// where ncclReduce's ring takes ~0.26 ms.  `buf` holds world * chunk floats; in place; on return the root's buf is the sum.
+int comm_reduce_sum_via_scatter(trace_ctx* c, float* buf, size_t chunk, int root) {
+    NcclApi* a = nccl_api();
+    if (!c->comm) return c->fail("no communicator: call trace_comm_init first");
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    TR_NCCL(c, a->ReduceScatter(buf, buf + (size_t)c->rank * chunk, chunk, ncclFloat, ncclSum, comm, c->stream));
+    TR_NCCL(c, a->GroupStart());
+    ncclResult_t r = ncclSuccess;
+    if (c->rank == root) {
+        for (int p = 0; p < c->world && r == ncclSuccess; ++p)
+            if (p != root) r = a->Recv(buf + (size_t)p * chunk, chunk, ncclFloat, p, comm, c->stream);
+    } else r = a->Send(buf + (size_t)c->rank * chunk, chunk, ncclFloat, root, comm, c->stream);
+    const ncclResult_t e = a->GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(c, "ncclSend / ncclRecv", r);
+    if (e != ncclSuccess) return nccl_fail(c, "ncclGroupEnd", e);
     return 0;
 }

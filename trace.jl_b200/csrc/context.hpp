@@ -81,7 +81,7 @@ struct trace_ctx {
     int rank = 0, world = 1;
     void* comm = nullptr;         // ncclComm_t of this rank (comm.cpp), null until trace_comm_init
     int nccl_version = 0;
-    int film_sum = 0;             // film_mode 0: 0 = ncclReduce to rank 0, 1 = ncclAllReduce (every rank ends up with the sum; rank 0 uses it)
+    int film_sum = 2;             // film_mode 0: 0 = ncclReduce to rank 0, 1 = ncclAllReduce, 2 = reduce-scatter + gather of the chunks onto rank 0
     int film_mode = 0;            // multi-rank Whitted film delivery: 0 = whole film summed onto rank 0, 1 = row bands (reduce-scatter)
     // CUDA graph of one Whitted render (all lanes, all batches): a render is ~20 launches per batch and the host
     // needs ~4.5 us per launch, which bounds small renders (1/8 of a frame per GPU) - replaying a captured graph does
@@ -249,6 +249,7 @@ int comm_reduce_sum(trace_ctx* ctx, const float* send, float* recv, size_t count
 int comm_reduce_scatter_sum(trace_ctx* ctx, const float* send, float* recv, size_t recv_count);
 int comm_allreduce_sum(trace_ctx* ctx, float* buf, size_t count);
 int comm_allgather(trace_ctx* ctx, const float* send, float* recv, size_t send_count);
+int comm_reduce_sum_via_scatter(trace_ctx* ctx, float* buf, size_t chunk, int root);
 int comm_group_begin(trace_ctx* ctx);
 int comm_group_end(trace_ctx* ctx);
 // implemented in whitted.cu / sppm.cu

@@ -1196,15 +1196,21 @@ static int sppm_iteration_async(trace_ctx* c, int it) {
         const size_t slice = (size_t)L.nstore / (size_t)c->world * 4;
         const SppmLaunch& S = s->slotL[s->cur_slot];
         float4* arr[5] = {S.vpA, S.vpB, S.vpC, S.vpD, S.vpE};
+        c->kev_begin(TRACE_K_COMM);
         if (comm_group_begin(c)) return 1;                       // one NCCL launch for the five arrays
         for (int k = 0; k < 5; ++k) {
             float* base = reinterpret_cast<float*>(arr[k]);
             if (comm_allgather(c, base + (size_t)c->rank * slice, base, slice)) { comm_group_end(c); return 1; }
         }
         if (comm_group_end(c)) return 1;
+        c->kev_end();
     }
     if (sppm_build_grid_async(c) || trace_sppm_photon_pass(c, it, b, e)) return 1;
-    if (multi && comm_allreduce_sum(c, reinterpret_cast<float*>(L.flux), (size_t)L.nstore * 4)) return 1;
+    if (multi) {
+        c->kev_begin(TRACE_K_COMM);
+        if (comm_allreduce_sum(c, reinterpret_cast<float*>(L.flux), (size_t)L.nstore * 4)) return 1;
+        c->kev_end();
+    }
     return trace_sppm_update(c);
 }
 
