@@ -65,6 +65,12 @@ extern "C" int trace_create(trace_ctx** out, int device, void* cuda_stream) {
     ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        ok = ok && cudaStreamCreateWithPriority(&c->chain_stream, cudaStreamNonBlocking, greatest) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&c->ev_chain, cudaEventDisableTiming) == cudaSuccess;
+    }
     for (int l = 0; l < trace_ctx::MAX_LANES && ok; ++l)
         ok = cudaStreamCreateWithFlags(&c->side[l], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming) == cudaSuccess;
@@ -92,6 +98,8 @@ extern "C" void trace_destroy(trace_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->chain_stream) cudaStreamDestroy(c->chain_stream);
+    if (c->ev_chain) cudaEventDestroy(c->ev_chain);
     if (c->wh_graph) cudaGraphExecDestroy(c->wh_graph);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -121,6 +129,7 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "time_kernels")) c->time_kernels = v != 0;
     else if (!strcmp(key, "graph")) c->graph = v != 0;
     else if (!strcmp(key, "sppm_lanes")) { if (v < 0 || v > trace_ctx::MAX_LANES / 2) return c->fail("sppm_lanes must be in [0, 8]"); c->sppm_lanes = (int)v; }
+    else if (!strcmp(key, "sppm_chain_priority")) c->sppm_chain_priority = v != 0;
     else if (!strcmp(key, "sppm_pipeline")) { if (v < 1 || v > 8) return c->fail("sppm_pipeline must be in [1, 8]"); c->sppm_pipeline = (int)v; }
     else if (!strcmp(key, "deal")) c->deal = (int)v;
     else if (!strcmp(key, "rank")) { if (c->comm) return c->fail("rank is fixed by trace_comm_init"); c->rank = (int)v; }

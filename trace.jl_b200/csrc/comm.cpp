@@ -152,6 +152,12 @@ int comm_allreduce_sum(trace_ctx* c, float* buf, size_t count) {
     TR_NCCL(c, a->AllReduce(buf, buf, count, ncclFloat, ncclSum, (ncclComm_t)c->comm, c->stream));
     return 0;
 }
+int comm_allreduce_sum_int(trace_ctx* c, int* buf, size_t count) {
+    NcclApi* a = nccl_api();
+    if (!c->comm) return c->fail("no communicator: call trace_comm_init first");
+    TR_NCCL(c, a->AllReduce(buf, buf, count, ncclInt, ncclSum, (ncclComm_t)c->comm, c->stream));
+    return 0;
+}
 int comm_allgather(trace_ctx* c, const float* send, float* recv, size_t send_count) {
     NcclApi* a = nccl_api();
     if (!c->comm) return c->fail("no communicator: call trace_comm_init first");

@@ -57,6 +57,11 @@ struct trace_ctx {
     static const int MAX_LANES = 16;
     cudaStream_t side[MAX_LANES] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {};
+    // the serial chain of an SPPM iteration (grid -> deposits -> all-reduce -> update) runs on a stream of the greatest
+    // priority: its launches overtake the run-ahead camera / photon launches of later iterations when CTA slots free up
+    cudaStream_t chain_stream = nullptr;
+    cudaEvent_t ev_chain = nullptr;
+    int sppm_chain_priority = 1;            // option: 0 keeps the chain on the caller's stream
     cudaStream_t copy_stream = nullptr;     // host film upload of trace_render_whitted, overlapped with the render
     cudaEvent_t ev_copy = nullptr;
     bool film_upload_pending = false;       // the film merge must wait for ev_copy
@@ -248,6 +253,7 @@ int ctx_pull_stats(trace_ctx* ctx);
 int comm_reduce_sum(trace_ctx* ctx, const float* send, float* recv, size_t count, int root);
 int comm_reduce_scatter_sum(trace_ctx* ctx, const float* send, float* recv, size_t recv_count);
 int comm_allreduce_sum(trace_ctx* ctx, float* buf, size_t count);
+int comm_allreduce_sum_int(trace_ctx* ctx, int* buf, size_t count);
 int comm_allgather(trace_ctx* ctx, const float* send, float* recv, size_t send_count);
 int comm_reduce_sum_via_scatter(trace_ctx* ctx, float* buf, size_t chunk, int root);
 int comm_group_begin(trace_ctx* ctx);

@@ -1189,6 +1189,23 @@ static int sppm_iteration_async(trace_ctx* c, int it) {
     const int64_t P = L.photons_per_iteration;
     const int64_t b = multi ? P * c->rank / c->world : 0, e = multi ? P * (c->rank + 1) / c->world : P;
     struct Flag { bool& f; explicit Flag(bool& f_) : f(f_) { f = true; } ~Flag() { f = false; } } pipelined(s->pipelined);
+    // The iteration is enqueued on the context's high-priority chain stream, forked from / joined into the caller's
+    // stream (so the caller's stream still orders everything): while this scope lives, c->stream IS the chain stream.
+    struct ChainScope {
+        trace_ctx* c; cudaStream_t caller; bool on;
+        explicit ChainScope(trace_ctx* c_) : c(c_), caller(c_->stream), on(c_->sppm_chain_priority && c_->chain_stream) {
+            if (!on) return;
+            cudaEventRecord(c->ev_chain, caller);
+            cudaStreamWaitEvent(c->chain_stream, c->ev_chain, 0);
+            c->stream = c->cur_stream = c->chain_stream;
+        }
+        ~ChainScope() {
+            if (!on) return;
+            cudaEventRecord(c->ev_chain, c->chain_stream);
+            cudaStreamWaitEvent(caller, c->ev_chain, 0);
+            c->stream = c->cur_stream = caller;
+        }
+    } chain(c);
     // photon tracing first: it does not need the grid and overlaps the camera pass (and the all-gather) on its own stream
     if (trace_sppm_trace_photons(c, it, b, e) || sppm_camera_pass_async(c, it)) return 1;
     if (multi) {

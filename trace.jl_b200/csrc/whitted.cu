@@ -371,12 +371,13 @@ __global__ void k_film_finalize(const float4* __restrict__ rgbw, float4* __restr
     }
 }
 
-// any[0] = 1 when one of the render's batches overflowed or a traversal ran out of stack
+// any[0] = 1 when one of the render's batches overflowed or a traversal ran out of stack, any[1] = 1 for the latter alone
+// (with a communicator the pair is summed over the ranks, so that all of them take the same path afterwards)
 __global__ void k_wh_any_flag(const int* __restrict__ batch_flags, int n, const int* __restrict__ error_flag, int* __restrict__ any) {
     int bad = 0;
     for (int i = threadIdx.x; i < n; i += 32) bad |= batch_flags[i];
     bad = __any_sync(0xffffffffu, bad != 0);
-    if (threadIdx.x == 0) *any = (bad || *error_flag) ? 1 : 0;
+    if (threadIdx.x == 0) { any[0] = (bad || *error_flag) ? 1 : 0; any[1] = *error_flag ? 1 : 0; }
 }
 
 __global__ void k_wh_batch_stats(int* counters, unsigned long long* stats, int max_depth, int cap_rays, int cap_shadow,
@@ -558,7 +559,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
         W.accum = c->b_queue[10].as<float4>() + (size_t)l * batch; W.filmpos = c->b_queue[11].as<float2>() + (size_t)l * batch;
         W.counters = ctx_icounters_lane(c, l);
     }
-    TR_CUDA(c, c->b_misc[2].ensure((size_t)(nb + 1) * sizeof(int)));
+    TR_CUDA(c, c->b_misc[2].ensure((size_t)(nb + 2) * sizeof(int)));
     int* d_flags = c->b_misc[2].as<int>();
     TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     // everything up to the lanes' join: film clear, then batch bi on lane bi % K
@@ -621,62 +622,65 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     const bool multi = c->comm != nullptr && c->world > 1;
     long long f0 = 0, f1 = (long long)npix;                     // film pixels this rank delivers
     whitted_film_range(c, (long long)npix, &f0, &f1);
-    // fold the flags, [single rank: merge the film unless something went wrong,] read the flags back
+    // The ONE exchange of a multi-rank render: the sum of the ranks' private films, on the render's stream.
+    auto film_sum = [&]() -> int {
+        TrRange nvtx_sum("whitted.film sum (NCCL)");
+        float* rgbw = reinterpret_cast<float*>(L.film_rgbw);
+        c->kev_begin(TRACE_K_COMM);
+        int rc2 = 0;
+        if (c->film_mode == 0) {
+            // whole film onto rank 0 (option film_sum): 0 ncclReduce, 1 ncclAllReduce, 2 (default) reduce-scatter + gather of
+            // the summed chunks - measured on 8 B200: ncclReduce of the 33 MB film 0.26 ms, all-reduce no better
+            if (c->film_sum == 1) rc2 = comm_allreduce_sum(c, rgbw, npix * 4);
+            else if (c->film_sum == 2) rc2 = comm_reduce_sum_via_scatter(c, rgbw, (npix + (size_t)c->world - 1) / (size_t)c->world * 4, 0);
+            else rc2 = comm_reduce_sum(c, rgbw, rgbw, npix * 4, 0);
+        } else {
+            const size_t chunk = (npix + (size_t)c->world - 1) / (size_t)c->world;
+            rc2 = comm_reduce_scatter_sum(c, rgbw, rgbw + (size_t)c->rank * chunk * 4, chunk * 4);     // in place
+        }
+        c->kev_end();
+        return rc2;
+    };
+    // Fold the flags and - optimistically - merge the film behind the render: ONE host wait per render.  k_film_finalize
+    // skips the merge when the (with a communicator: rank-summed) flag says that something went wrong somewhere.
     k_wh_any_flag<<<1, 32, 0, c->stream>>>(d_flags, (int)nb, d_err, d_flags + nb);
     c->stats.kernel_launches++;
-    if (!multi) {
-        // optimistic: the merge is already enqueued behind the render - ONE host wait per render
-        if (c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
-        k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix, d_flags + nb);
-        c->stats.kernel_launches++;
-        TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    if (multi) {
+        if (comm_allreduce_sum_int(c, d_flags + nb, 2)) return 1;          // every rank learns whether ANY rank has to redo batches
+        if (film_sum()) return 1;
     }
+    if (f1 > f0) {
+        if (c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
+        k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw + f0, (float4*)film_dev + f0, (int)(f1 - f0), d_flags + nb);
+        c->stats.kernel_launches++;
+    }
+    TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     std::vector<int> h_flags((size_t)nb + 2, 0);
-    TR_CUDA(c, cudaMemcpyAsync(h_flags.data(), d_flags, (size_t)(nb + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    TR_CUDA(c, cudaMemcpyAsync(&h_flags[(size_t)nb + 1], d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(c, cudaMemcpyAsync(h_flags.data(), d_flags, (size_t)(nb + 2) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     TR_CUDA(c, cudaStreamSynchronize(c->stream));
     c->kev_collect();
-    if (h_flags[(size_t)nb + 1]) {
+    if (h_flags[(size_t)nb + 1]) {                              // (rank-summed: every rank fails together)
         cudaMemsetAsync(d_err, 0, sizeof(int), c->stream);
-        // (multi-rank: the other ranks are left waiting in the film sum - a traversal error is fatal for the job)
         return c->fail("traversal stack overflow (more than 64 pending nodes; the reference would throw a BoundsError, bvh.jl:222)");
     }
     if (h_flags[(size_t)nb]) {
+        // A ray queue overflowed somewhere (rare: the queues hold cap_percent = 200 % of a batch): nothing has been merged.
+        // Overflowed batches were not splatted: redo them in halves.  With a communicator the private film already went
+        // through the (discarded) sum, so this rank's film is rebuilt from scratch, then summed and merged again.
+        if (multi) {
+            TR_CUDA(c, cudaMemsetAsync(L.film_rgbw, 0, npix_padded * sizeof(float4), c->stream));
+            c->cur_lane = 0; c->cur_stream = c->stream;
+        }
         for (long long bi = 0; bi < nb; ++bi) {
-            if (!h_flags[bi]) continue;                     // overflowed batches were not splatted: redo them in halves
+            if (!h_flags[bi]) { if (multi && run_batch(c, lane[0], b_begin[bi], b_count[bi], 1)) return 1; continue; }
             c->stats.queue_overflows++;
             const long long b = b_begin[bi], cnt = b_count[bi], half = cnt / 2 / per_tile * per_tile;
             if (cnt < 2 * per_tile) return c->fail("ray queue overflow that halving the batch cannot resolve");
             if (run_batch(c, lane[0], b, half, 1) || run_batch(c, lane[0], b + half, cnt - half, 1)) return 1;
         }
-        if (!multi) {
-            k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw, (float4*)film_dev, (int)npix, nullptr);
-            c->stats.kernel_launches++;
-            TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-            TR_CUDA(c, cudaStreamSynchronize(c->stream));
-        }
-    }
-    if (multi) {
-        // the ONE exchange of a Whitted render: sum of the ranks' private films, on the render's stream
-        TrRange nvtx_sum("whitted.film sum (NCCL)");
-        float* rgbw = reinterpret_cast<float*>(L.film_rgbw);
-        const float4* merged = L.film_rgbw;
-        c->kev_begin(TRACE_K_COMM);
-        if (c->film_mode == 0) {
-            // whole film onto rank 0 (option film_sum): 0 ncclReduce, 1 ncclAllReduce, 2 (default) reduce-scatter + gather of
-            // the summed chunks - measured on 8 B200: ncclReduce of the 33 MB film 0.26 ms, all-reduce no better
-            if (c->film_sum == 1) { if (comm_allreduce_sum(c, rgbw, npix * 4)) return 1; }
-            else if (c->film_sum == 2) { if (comm_reduce_sum_via_scatter(c, rgbw, (npix + (size_t)c->world - 1) / (size_t)c->world * 4, 0)) return 1; }
-            else if (comm_reduce_sum(c, rgbw, rgbw, npix * 4, 0)) return 1;
-        }
-        else {
-            const size_t chunk = (npix + (size_t)c->world - 1) / (size_t)c->world;
-            if (comm_reduce_scatter_sum(c, rgbw, rgbw + (size_t)c->rank * chunk * 4, chunk * 4)) return 1;     // in place
-        }
-        c->kev_end();
+        if (multi && film_sum()) return 1;
         if (f1 > f0) {
-            if (c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
-            k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(merged + f0, (float4*)film_dev + f0, (int)(f1 - f0), nullptr);
+            k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw + f0, (float4*)film_dev + f0, (int)(f1 - f0), nullptr);
             c->stats.kernel_launches++;
         }
         TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
