@@ -78,6 +78,38 @@ def main():
         ok &= np.allclose(whole, want, rtol=2e-4, atol=1e-5)
     ctx.set_option("film_mode", 0)
 
+    # A ray queue that overflows on some rank: every rank must take the redo path together (rank-summed flags) and the image
+    # must still equal the one-GPU render.  Glass spawns two rays per hit, so with the queues squeezed to 100 % of a batch
+    # bounce level 2 overflows (tests/test_gpu_parity.py has the one-GPU form of this case).
+    glass = T.GlassMaterial(T.ConstantTexture(T.RGBSpectrum(1.0)), T.ConstantTexture(T.RGBSpectrum(1.0)), T.ConstantTexture(0.0),
+                            T.ConstantTexture(0.0), T.ConstantTexture(1.5), True)
+    white = T.MatteMaterial(T.ConstantTexture(T.RGBSpectrum(1.0)), T.ConstantTexture(0.0))
+    prims = [T.GeometricPrimitive(T.Sphere(T.ShapeCore(T.translate([0.5, 0.5, -2.5]), False), 0.55, 360.0), glass)]
+    tris = T.create_triangle_mesh(T.ShapeCore(T.translate([0, 0, -2]), False), 2, [1, 2, 3, 1, 4, 3], 4,
+                                  [[-2, -0.2, 2], [-2, -0.2, -3], [3, -0.2, -3], [3, -0.2, 2]], [[0, 1, 0]] * 4)
+    prims += [T.GeometricPrimitive(t, white) for t in tris]
+    o_scene = T.Scene([T.PointLight(T.translate([-1, 3, 0]), T.RGBSpectrum(25.0))], T.BVHAccel(prims, 1))
+    o_film = T.Film([128, 128], T.Bounds2([0, 0], [1, 1]), T.LanczosSincFilter([1, 1], 3.0), 1.0, 1.0, None)
+    o_cam = T.PerspectiveCamera(T.look_at([0, 15, 50], [0, 0, -2], [0, 1, 0]), T.Bounds2([-1, -1], [1, 1]), 0, 1, 0, 1e6, 90.0, o_film)
+    oc, of = o_cam.pod(), o_film.desc()
+    ctx.upload(o_scene)
+    ctx.set_option("cap_percent", 100)
+    ctx.set_option("batch", 8192)
+    ctx.reset_stats()
+    got = np.zeros_like(o_film.pixels)
+    ctx.check(ctx.lib.trace_render_whitted(ctx.h, C.byref(oc), C.byref(of), 4, 8, C.c_uint64(5), T._lib.ptr(got) if rank == 0 else None))
+    n_over = torch.tensor([float(ctx.stats()["queue_overflows"])], device=f"cuda:{local}")
+    dist.all_reduce(n_over)
+    ctx.set_option("batch", 1 << 26)
+    ctx.set_option("cap_percent", 200)
+    if rank == 0:
+        solo.upload(o_scene)
+        want_o = np.zeros_like(got)
+        solo.check(solo.lib.trace_render_whitted(solo.h, C.byref(oc), C.byref(of), 4, 8, C.c_uint64(5), T._lib.ptr(want_o)))
+        report["overflow_redo_batches_all_ranks"] = int(n_over.item())
+        report["overflow_redo_max_rel_err"] = float(np.abs(got - want_o).max() / np.abs(want_o).max())
+        ok &= np.allclose(got, want_o, rtol=2e-4, atol=1e-5) and n_over.item() > 0
+
     # SPPM over all ranks vs one GPU (two scenes: spheres; the two-light caustic scene when the asset is there)
     cases = [("shadows", T.scenes.shadows(resolution=151), 3, -1)]
     if os.path.exists(T.scenes.ASSET_PLY):

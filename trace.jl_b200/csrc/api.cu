@@ -69,6 +69,7 @@ extern "C" int trace_create(trace_ctx** out, int device, void* cuda_stream) {
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
         ok = ok && cudaStreamCreateWithPriority(&c->chain_stream, cudaStreamNonBlocking, greatest) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&c->coll_stream, cudaStreamNonBlocking, greatest) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&c->ev_chain, cudaEventDisableTiming) == cudaSuccess;
     }
     for (int l = 0; l < trace_ctx::MAX_LANES && ok; ++l)
@@ -99,6 +100,7 @@ extern "C" void trace_destroy(trace_ctx* c) {
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->chain_stream) cudaStreamDestroy(c->chain_stream);
+    if (c->coll_stream) cudaStreamDestroy(c->coll_stream);
     if (c->ev_chain) cudaEventDestroy(c->ev_chain);
     if (c->wh_graph) cudaGraphExecDestroy(c->wh_graph);
     if (c->h_flags) cudaFreeHost(c->h_flags);

@@ -60,6 +60,7 @@ struct trace_ctx {
     // the serial chain of an SPPM iteration (grid -> deposits -> all-reduce -> update) runs on a stream of the greatest
     // priority: its launches overtake the run-ahead camera / photon launches of later iterations when CTA slots free up
     cudaStream_t chain_stream = nullptr;
+    cudaStream_t coll_stream = nullptr;     // SPPM collectives (same priority): the next all-gather overlaps this iteration's chain
     cudaEvent_t ev_chain = nullptr;
     int sppm_chain_priority = 1;            // option: 0 keeps the chain on the caller's stream
     cudaStream_t copy_stream = nullptr;     // host film upload of trace_render_whitted, overlapped with the render

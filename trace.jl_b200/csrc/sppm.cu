@@ -667,8 +667,9 @@ struct SppmState {
     int Kc = 1, Kp = 1;             // camera lanes use the context's lane ids 0..Kc-1, photon lanes Kc..Kc+Kp-1
     std::vector<SppmLaunch> cam_lane, ph_lane;
     cudaEvent_t ev_ph_fork = nullptr, ev_grid = nullptr;
-    int traced_it = -1;             // photon tracing already enqueued for this iteration / range
-    int64_t traced_begin = 0, traced_end = 0;
+    struct Traced { int it = -1; int64_t begin = 0, end = 0; } traced[SPPM_MAX_SLOTS];   // photon tracing already enqueued (per slot)
+    cudaEvent_t ev_gathered[SPPM_MAX_SLOTS] = {};      // the slot's visible points are complete on this rank (all-gather done)
+    cudaEvent_t ev_deposited = nullptr, ev_reduced = nullptr;
     bool active = false;
 };
 
@@ -678,6 +679,9 @@ void sppm_free(trace_ctx* c) {                 // releases the device memory too
     for (auto& b : s->pix) b.release();
     for (auto& sl : s->vp_extra) for (auto& b : sl) b.release();
     for (auto& e : s->ev_slot_free) if (e) cudaEventDestroy(e);
+    for (auto& e : s->ev_gathered) if (e) cudaEventDestroy(e);
+    if (s->ev_deposited) cudaEventDestroy(s->ev_deposited);
+    if (s->ev_reduced) cudaEventDestroy(s->ev_reduced);
     for (auto& b : s->cells) b.release();
     for (auto& b : s->q) b.release();
     for (auto& b : s->pq) b.release();
@@ -690,7 +694,7 @@ void sppm_free(trace_ctx* c) {                 // releases the device memory too
 // ends a session but keeps the (grow-only) buffers: a caller rendering frame after frame (docs/code/caustic_moving.jl:
 // 51 frames) does not pay ~1 GB of cudaMalloc / cudaFree per trace_render_sppm
 void sppm_end_session(trace_ctx* c) {
-    if (c->sppm) { c->sppm->active = false; c->sppm->traced_it = -1; }
+    if (c->sppm) { c->sppm->active = false; for (auto& t : c->sppm->traced) t.it = -1; }
 }
 
 static float host_luminance_power(const trace_ctx*, const DeviceLight& l) {       // to_Y(power(light)), sppm.jl:564-569
@@ -767,8 +771,12 @@ extern "C" int trace_sppm_begin(trace_ctx* c, const trace_camera* cam, const tra
     // iterations in flight (see SppmState): every slot needs Kc + Kp lanes (streams, counter blocks)
     s->D = std::max(1, std::min(std::min(c->sppm_pipeline, SPPM_MAX_SLOTS), trace_ctx::MAX_LANES / (s->Kc + s->Kp)));
     s->cur_slot = 0; s->pipelined = false;
-    for (int d = 0; d < s->D; ++d)
+    for (int d = 0; d < s->D; ++d) {
         if (!s->ev_slot_free[d]) TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_slot_free[d], cudaEventDisableTiming));
+        if (!s->ev_gathered[d]) TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_gathered[d], cudaEventDisableTiming));
+    }
+    if (!s->ev_deposited) TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_deposited, cudaEventDisableTiming));
+    if (!s->ev_reduced) TR_CUDA(c, cudaEventCreateWithFlags(&s->ev_reduced, cudaEventDisableTiming));
     for (int d = 1; d < s->D; ++d)
         for (int k = 0; k < 5; ++k) {
             TR_CUDA(c, s->vp_extra[d][k].ensure(f4b));
@@ -928,7 +936,8 @@ static int sppm_camera_lane(trace_ctx* c, SppmState* s, int l, int iteration) {
 }
 
 // camera pass of this rank's rows, enqueued only (no host wait)
-static int sppm_camera_pass_async(trace_ctx* c, int iteration) {
+// `join` false: the caller makes whoever needs the visible points wait for the slot's lanes (sppm_join_camera)
+static int sppm_camera_pass_async(trace_ctx* c, int iteration, bool join = true) {
     if (!c) return 1;
     cudaSetDevice(c->device);
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_camera_pass: call trace_sppm_begin first");
@@ -945,16 +954,21 @@ static int sppm_camera_pass_async(trace_ctx* c, int iteration) {
         LaneScope scope(c, lane, c->side[lane]);
         if (sppm_camera_lane(c, s, lane, iteration)) return 1;
         TR_CUDA(c, cudaEventRecord(c->ev_join[lane], c->side[lane]));
-        TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[lane], 0));
+        if (join) TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join[lane], 0));
     }
     TR_CUDA(c, cudaGetLastError());
+    return 0;
+}
+static int sppm_join_camera(trace_ctx* c, int slot, cudaStream_t waiter) {
+    SppmState* s = c->sppm;
+    for (int l = 0; l < s->Kc; ++l) TR_CUDA(c, cudaStreamWaitEvent(waiter, c->ev_join[slot * s->Kc + l], 0));
     return 0;
 }
 
 static int sppm_build_grid_async(trace_ctx* c);
 
 extern "C" int trace_sppm_camera_pass(trace_ctx* c, int iteration) {
-    if (sppm_camera_pass_async(c, iteration)) return 1;
+    if (sppm_camera_pass_async(c, iteration, true)) return 1;
     if (c->world > 1) return check_flags(c, "trace_sppm_camera_pass");   // caller all-gathers the visible points, then build_grid
     return trace_sppm_build_grid(c);
 }
@@ -1065,7 +1079,8 @@ extern "C" int trace_sppm_trace_photons(trace_ctx* c, int iteration, int64_t beg
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_trace_photons: call trace_sppm_begin first");
     SppmState* s = c->sppm;
     if (begin < 0 || end > s->L.photons_per_iteration || begin > end) return c->fail("trace_sppm_trace_photons: bad photon range");
-    s->traced_it = -1;
+    const int tslot = s->pipelined ? (iteration - 1) % s->D : 0;
+    s->traced[tslot].it = -1;
     if (end - begin > (int64_t)s->photon_cap * s->Kp) return 0;          // does not fit: photon_pass will chunk it
     const int64_t per = (end - begin + s->Kp - 1) / s->Kp;
     // Photon paths read nothing an earlier iteration writes; the lane's own stream orders them after the deposits that
@@ -1081,7 +1096,7 @@ extern "C" int trace_sppm_trace_photons(trace_ctx* c, int iteration, int64_t beg
         if (sppm_trace_lane(c, s, idx, iteration, b, (int)(e - b))) return 1;
     }
     TR_CUDA(c, cudaGetLastError());
-    s->traced_it = iteration; s->traced_begin = begin; s->traced_end = end;
+    s->traced[tslot].it = iteration; s->traced[tslot].begin = begin; s->traced[tslot].end = end;
     return 0;
 }
 
@@ -1095,9 +1110,10 @@ extern "C" int trace_sppm_photon_pass(trace_ctx* c, int iteration, int64_t begin
     const int64_t chunk = (int64_t)s->photon_cap * s->Kp;
     for (int64_t b0 = begin;; b0 += chunk) {
         const int64_t e0 = std::min(end, b0 + chunk);
-        if (!(s->traced_it == iteration && s->traced_begin == b0 && s->traced_end == e0))
+        SppmState::Traced& tr = s->traced[s->pipelined ? (iteration - 1) % s->D : 0];
+        if (!(tr.it == iteration && tr.begin == b0 && tr.end == e0))
             if (trace_sppm_trace_photons(c, iteration, b0, e0)) return 1;
-        s->traced_it = -1;
+        tr.it = -1;
         // the deposits need the grid (main stream): every photon lane waits for it, deposits, and joins the main stream
         TR_CUDA(c, cudaEventRecord(s->ev_grid, c->stream));
         const int slot = s->pipelined ? (iteration - 1) % s->D : 0;
@@ -1178,19 +1194,84 @@ extern "C" int trace_sppm_end(trace_ctx* c) {
     return 0;
 }
 
-// One SPPM iteration (sppm.jl:153-165) enqueued on the context's streams without any host wait.  With a communicator
-// the two exchange steps of SURVEY.md 8e run here: all-gather of the visible points (camera paths are sharded by image
-// rows) and all-reduce(sum) of (Phi, M) (photons are sharded by index range).
-static int sppm_iteration_async(trace_ctx* c, int it) {
-    TrRange nvtx("sppm.iteration");
+// SPPM iterations (sppm.jl:153-165) enqueued on the context's streams without any host wait.  An iteration is two phases:
+//   A  photon tracing + camera pass on the slot's own streams, and - with a communicator - the all-gather of the
+//      visible points (camera paths are sharded by image rows) on the COLLECTIVE stream;
+//   B  the serial chain on the main stream: hash grid -> deposits -> all-reduce(sum) of (Phi, M) (photons are sharded by
+//      index range; collective stream) -> update.
+// Phase A of iteration it + 1 is enqueued BEFORE phase B of iteration it: NCCL runs a communicator's operations in
+// issue order, so the next all-gather then sits in front of this iteration's all-reduce and overlaps the chain instead of
+// extending it (measured on 8 B200, caustic_moving: the chain - all-gather 0.25 + grid 0.33 + deposits 0.1 + all-reduce
+// 0.25 ms - was the whole iteration).  Needs two slots (the look-ahead pass must not reuse the slot in flight).
+static int sppm_phase_a(trace_ctx* c, int it) {
     SppmState* s = c->sppm;
     SppmLaunch& L = s->L;
     const bool multi = c->comm != nullptr && c->world > 1;
     const int64_t P = L.photons_per_iteration;
     const int64_t b = multi ? P * c->rank / c->world : 0, e = multi ? P * (c->rank + 1) / c->world : P;
+    // photon tracing first: it does not need the grid and overlaps the camera pass (and the all-gather) on its own stream
+    if (trace_sppm_trace_photons(c, it, b, e) || sppm_camera_pass_async(c, it, false)) return 1;
+    const int slot = s->cur_slot;
+    if (!multi) return 0;
+    // rank r owns slice r of every per-pixel array (storage order): five in-place all-gathers, one NCCL launch
+    if (sppm_join_camera(c, slot, c->coll_stream)) return 1;
+    const size_t slice = (size_t)L.nstore / (size_t)c->world * 4;
+    const SppmLaunch& S = s->slotL[slot];
+    float4* arr[5] = {S.vpA, S.vpB, S.vpC, S.vpD, S.vpE};
+    struct CollScope {
+        trace_ctx* c; cudaStream_t saved, saved_cur;
+        explicit CollScope(trace_ctx* c_) : c(c_), saved(c_->stream), saved_cur(c_->cur_stream) { c->stream = c->cur_stream = c->coll_stream; }
+        ~CollScope() { c->stream = saved; c->cur_stream = saved_cur; }
+    } coll(c);
+    c->kev_begin(TRACE_K_COMM);
+    if (comm_group_begin(c)) return 1;
+    for (int k = 0; k < 5; ++k) {
+        float* base = reinterpret_cast<float*>(arr[k]);
+        if (comm_allgather(c, base + (size_t)c->rank * slice, base, slice)) { comm_group_end(c); return 1; }
+    }
+    if (comm_group_end(c)) return 1;
+    c->kev_end();
+    TR_CUDA(c, cudaEventRecord(s->ev_gathered[slot], c->coll_stream));
+    return 0;
+}
+
+static int sppm_phase_b(trace_ctx* c, int it) {
+    SppmState* s = c->sppm;
+    SppmLaunch& L = s->L;
+    const bool multi = c->comm != nullptr && c->world > 1;
+    const int64_t P = L.photons_per_iteration;
+    const int64_t b = multi ? P * c->rank / c->world : 0, e = multi ? P * (c->rank + 1) / c->world : P;
+    const int slot = (it - 1) % s->D;
+    s->cur_slot = slot;                                          // (phase A of the next iteration moved it on)
+    if (multi) TR_CUDA(c, cudaStreamWaitEvent(c->stream, s->ev_gathered[slot], 0));
+    else if (sppm_join_camera(c, slot, c->stream)) return 1;
+    if (sppm_build_grid_async(c) || trace_sppm_photon_pass(c, it, b, e)) return 1;
+    if (multi) {
+        TR_CUDA(c, cudaEventRecord(s->ev_deposited, c->stream));
+        TR_CUDA(c, cudaStreamWaitEvent(c->coll_stream, s->ev_deposited, 0));
+        {
+            cudaStream_t saved = c->stream, saved_cur = c->cur_stream;
+            c->stream = c->cur_stream = c->coll_stream;
+            c->kev_begin(TRACE_K_COMM);
+            const int rc = comm_allreduce_sum(c, reinterpret_cast<float*>(L.flux), (size_t)L.nstore * 4);
+            c->kev_end();
+            c->stream = saved; c->cur_stream = saved_cur;
+            if (rc) return 1;
+        }
+        TR_CUDA(c, cudaEventRecord(s->ev_reduced, c->coll_stream));
+        TR_CUDA(c, cudaStreamWaitEvent(c->stream, s->ev_reduced, 0));
+    }
+    return trace_sppm_update(c);
+}
+
+// iterations first .. first + n - 1
+static int sppm_iterations_async(trace_ctx* c, int first, int n) {
+    TrRange nvtx("sppm.iterations");
+    if (n <= 0) return 0;
+    SppmState* s = c->sppm;
     struct Flag { bool& f; explicit Flag(bool& f_) : f(f_) { f = true; } ~Flag() { f = false; } } pipelined(s->pipelined);
-    // The iteration is enqueued on the context's high-priority chain stream, forked from / joined into the caller's
-    // stream (so the caller's stream still orders everything): while this scope lives, c->stream IS the chain stream.
+    // Everything is enqueued on the context's high-priority chain stream, forked from / joined into the caller's stream
+    // (so the caller's stream still orders everything): while this scope lives, c->stream IS the chain stream.
     struct ChainScope {
         trace_ctx* c; cudaStream_t caller; bool on;
         explicit ChainScope(trace_ctx* c_) : c(c_), caller(c_->stream), on(c_->sppm_chain_priority && c_->chain_stream) {
@@ -1206,29 +1287,24 @@ static int sppm_iteration_async(trace_ctx* c, int it) {
             c->stream = c->cur_stream = caller;
         }
     } chain(c);
-    // photon tracing first: it does not need the grid and overlaps the camera pass (and the all-gather) on its own stream
-    if (trace_sppm_trace_photons(c, it, b, e) || sppm_camera_pass_async(c, it)) return 1;
-    if (multi) {
-        // rank r owns slice r of every per-pixel array (storage order): five in-place all-gathers of the visible points
-        const size_t slice = (size_t)L.nstore / (size_t)c->world * 4;
-        const SppmLaunch& S = s->slotL[s->cur_slot];
-        float4* arr[5] = {S.vpA, S.vpB, S.vpC, S.vpD, S.vpE};
-        c->kev_begin(TRACE_K_COMM);
-        if (comm_group_begin(c)) return 1;                       // one NCCL launch for the five arrays
-        for (int k = 0; k < 5; ++k) {
-            float* base = reinterpret_cast<float*>(arr[k]);
-            if (comm_allgather(c, base + (size_t)c->rank * slice, base, slice)) { comm_group_end(c); return 1; }
-        }
-        if (comm_group_end(c)) return 1;
-        c->kev_end();
+    const bool multi = c->comm != nullptr && c->world > 1;
+    if (multi) {                                                 // the collective stream starts behind whatever the caller enqueued
+        TR_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+        TR_CUDA(c, cudaStreamWaitEvent(c->coll_stream, c->ev_fork, 0));
     }
-    if (sppm_build_grid_async(c) || trace_sppm_photon_pass(c, it, b, e)) return 1;
-    if (multi) {
-        c->kev_begin(TRACE_K_COMM);
-        if (comm_allreduce_sum(c, reinterpret_cast<float*>(L.flux), (size_t)L.nstore * 4)) return 1;
-        c->kev_end();
+    const bool look_ahead = s->D >= 2;
+    const int last = first + n - 1;
+    if (sppm_phase_a(c, first)) return 1;
+    for (int it = first; it <= last; ++it) {
+        if (look_ahead && it < last && sppm_phase_a(c, it + 1)) return 1;
+        if (sppm_phase_b(c, it)) return 1;
+        if (!look_ahead && it < last && sppm_phase_a(c, it + 1)) return 1;
     }
-    return trace_sppm_update(c);
+    if (multi) {                                                 // ... and the caller's stream ends behind the collective stream
+        TR_CUDA(c, cudaEventRecord(c->ev_fork, c->coll_stream));
+        TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+    }
+    return 0;
 }
 
 extern "C" int trace_render_sppm(trace_ctx* c, const trace_camera* cam, const trace_film_desc* film, float r0, int max_depth,
@@ -1241,11 +1317,17 @@ extern "C" int trace_render_sppm(trace_ctx* c, const trace_camera* cam, const tr
         return c->fail("trace_render_sppm over several ranks needs trace_comm_init (or drive the stepwise trace_sppm_* API and do the exchanges yourself)");
     if (trace_sppm_begin(c, cam, film, r0, max_depth, photons, seed)) return 1;
     TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    for (int it = 1; it <= n_iterations; ++it) {
-        if (sppm_iteration_async(c, it)) { sppm_end_session(c); return 1; }
-        if (on_image && write_frequency > 0 && (it % write_frequency == 0) && it != n_iterations) {   // sppm.jl:167-171
-            if (trace_sppm_image(c, it, rgb_out)) { sppm_end_session(c); return 1; }
-            on_image(user, it, rgb_out);
+    // iterations are enqueued in runs that end where the caller wants an image (sppm.jl:167-171)
+    const bool stream_images = on_image && write_frequency > 0;
+    for (int it = 1; it <= n_iterations;) {
+        int run = n_iterations - it + 1;
+        if (stream_images) run = std::min(run, write_frequency - (it - 1) % write_frequency);
+        if (sppm_iterations_async(c, it, run)) { sppm_end_session(c); return 1; }
+        it += run;
+        const int done = it - 1;
+        if (stream_images && done % write_frequency == 0 && done != n_iterations) {
+            if (trace_sppm_image(c, done, rgb_out)) { sppm_end_session(c); return 1; }
+            on_image(user, done, rgb_out);
         }
     }
     TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
@@ -1266,7 +1348,5 @@ extern "C" int trace_sppm_iterate(trace_ctx* c, int first_iteration, int n) {
     if (!c->sppm || !c->sppm->active) return c->fail("trace_sppm_iterate: call trace_sppm_begin first");
     if (first_iteration < 1 || n < 0) return c->fail("trace_sppm_iterate: bad arguments");
     if (c->world != 1 && !c->comm) return c->fail("trace_sppm_iterate over several ranks needs trace_comm_init");
-    for (int it = first_iteration; it < first_iteration + n; ++it)
-        if (sppm_iteration_async(c, it)) return 1;
-    return 0;
+    return sppm_iterations_async(c, first_iteration, n);
 }
