@@ -172,7 +172,12 @@ const char* trace_last_error(const trace_ctx* ctx);
  *          of a Whitted render in flight concurrently on side streams (1..16, default 12); "deal" how tiles are dealt
  *          to those batches (g > 0: groups of g tiles, -r: r tile rows, 0: contiguous bands; default -2); "graph" 0/1
  *          replay the render as one CUDA graph (default 1; needs a non-default stream); "sppm_lanes" sub-ranges of
- *          each SPPM pass on concurrent streams (0..8, default 0 = one camera + one photon lane); "walk" traversal
+ *          each SPPM pass on concurrent streams (0..8, default 0 = one camera + one photon lane); "sppm_pipeline" SPPM
+ *          iterations in flight (1..8, default 4): the camera pass and the photon tracing of later iterations run on
+ *          their own streams and buffers while the serial chain grid -> deposits -> all-reduce -> update of the current
+ *          one runs ("sppm_chain_priority" 0/1, default 1: that chain on a high-priority stream); "film_sum" how the
+ *          whole film reaches rank 0 in film_mode 0: 0 ncclReduce, 1 ncclAllReduce, 2 reduce-scatter + gather of the
+ *          chunks (default); "walk" traversal
  *          loop: 1 = pair nodes (default: one 64-byte fetch serves both children's box tests and the far child is
  *          pushed with its entry distance; same hits bit for bit), 0 = one node per step exactly as
  *          src/accel/bvh.jl:221-257; "leaf_wait" 0/4/8/16/32 warp-synchronous variant of loop 0 with batched leaf
