@@ -87,7 +87,7 @@ struct trace_ctx {
     int rank = 0, world = 1;
     void* comm = nullptr;         // ncclComm_t of this rank (comm.cpp), null until trace_comm_init
     int nccl_version = 0;
-    int film_sum = 2;             // film_mode 0: 0 = ncclReduce to rank 0, 1 = ncclAllReduce, 2 = reduce-scatter + gather of the chunks onto rank 0
+    int film_sum = 0;             // film_mode 0: 0 = ncclReduce to rank 0, 1 = ncclAllReduce, 2 = reduce-scatter + gather of the chunks onto rank 0
     int film_mode = 0;            // multi-rank Whitted film delivery: 0 = whole film summed onto rank 0, 1 = row bands (reduce-scatter)
     // CUDA graph of one Whitted render (all lanes, all batches): a render is ~20 launches per batch and the host
     // needs ~4.5 us per launch, which bounds small renders (1/8 of a frame per GPU) - replaying a captured graph does
@@ -182,6 +182,7 @@ enum { ST_RAYS_EXTEND = 0, ST_RAYS_SHADOW = 1, ST_NODES = 2, ST_PRIMS = 3, ST_DE
 static const int TR_INT_COUNTERS = 128;    // ints at the start of b_counters (64..127: work counters of persistent launches)
 // int counter slots: [1 .. TR_MAX_DEPTH] ray-queue length per bounce level, [32] shadow / deposit-request queue
 enum { IC_OVERFLOW = 60, IC_ERROR = 61, IC_OVERFLOW_SHADOW = 62, IC_OVERFLOW_DEPOSIT = 63 };
+enum { IC_BACK = 33 };     // [IC_BACK + level]: rays pushed from the BACK of bounce level `level`'s queue (Whitted, wavefront.cuh)
 // deepest path any entry point accepts (the per-level queue counters live in slots 1..31 of a lane's counter block)
 static const int TR_MAX_DEPTH = 24;
 

@@ -15,15 +15,28 @@
 // WAIT: 0 = plain per-thread loop (traverse<>), > 0 = warp-synchronous loop with batched leaves (traverse_lb<>).
 // The grid-stride loop is warp-uniform (whole warps step together; lanes past the end of the queue are `valid ==
 // false`), which the warp-synchronous traversal needs and the plain one does not mind.
+// Two-ended queues (Whitted, bounce levels >= 2): a glass hit spawns a reflected AND a transmitted ray; pushed into one
+// queue they alternate in blocks and every warp of the next level walks two unrelated ray bundles (ncu: 10-12 of 32
+// lanes at the deep levels).  The shade stage therefore pushes reflected rays from the front (count) and transmitted
+// rays from the back (count_back) of the same array: entry j < nf sits at j, entry nf + k at cap - 1 - k, so warps are
+// homogeneous except the one that straddles the seam.  count_back == nullptr: a plain front-filled queue (SPPM).
+__device__ __forceinline__ int queue_position(int j, int nf, int cap) { return j < nf ? j : cap - 1 - (j - nf); }
+__device__ __forceinline__ void queue_extent(const int* count, const int* count_back, int cap, int& nf, int& n) {
+    nf = min(*count, cap);
+    n = nf + (count_back ? min(*count_back, cap - nf) : 0);
+}
+
 template <int SLAB, bool COUNT, int WAIT>
 __global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_extend(DeviceScene sc, const float4* __restrict__ ro, const float4* __restrict__ rd,
-                                                   const int* __restrict__ count, int cap, float4* __restrict__ hits,
-                                                   unsigned long long* counters, int* error_flag) {
-    const int n = min(*count, cap);
+                                                   const int* __restrict__ count, const int* __restrict__ count_back, int cap,
+                                                   float4* __restrict__ hits, unsigned long long* counters, int* error_flag) {
+    int nf, n;
+    queue_extent(count, count_back, cap, nf, n);
     const int lane = threadIdx.x & 31;
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += gridDim.x * blockDim.x) {
-        const int i = base + lane;
-        const bool valid = i < n;
+        const int j = base + lane;
+        const bool valid = j < n;
+        const int i = valid ? queue_position(j, nf, cap) : 0;
         const float4 o = valid ? q_load(&ro[i]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = valid ? q_load(&rd[i]) : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         HitRecord h;
         // closest hit; the third barycentric is rebuilt exactly in the shade stage from the winning triangle
@@ -82,8 +95,8 @@ static void launch_shadow_plain(trace_ctx* c, int grid, Args... args) {
 
 
 static void launch_extend(trace_ctx* c, int grid, DeviceScene sc, const float4* ro, const float4* rd, const int* count, int cap,
-                          float4* hits, unsigned long long* counters, int* err) {
-    launch_extend_plain(c, grid, sc, ro, rd, count, cap, hits, counters, err);
+                          float4* hits, unsigned long long* counters, int* err, const int* count_back = nullptr) {
+    launch_extend_plain(c, grid, sc, ro, rd, count, count_back, cap, hits, counters, err);
 }
 static void launch_shadow(trace_ctx* c, int grid, DeviceScene sc, const float4* so, const float4* sd, const float4* contrib,
                           const int* count, int cap, float4* accum, unsigned long long* counters, int* err) {

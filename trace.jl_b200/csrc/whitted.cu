@@ -147,10 +147,16 @@ __global__ void __launch_bounds__(128, TR_TRAV_MIN_BLOCKS) k_wh_primary(const __
 __global__ void __launch_bounds__(128, TR_SHADE_MIN_BLOCKS) k_wh_shade(WhittedLaunch L, int level) {
     const int cur = (level - 1) & 1, nxt = level & 1;
     const bool rederive = L.fused && level == 1;
-    const int n = rederive ? L.n_slots : min(L.counters[level], L.cap_rays);
+    // levels >= 2 read a two-ended queue (wavefront.cuh): reflected rays from the front, transmitted rays from the back
+    int nf, n;
+    queue_extent(&L.counters[level], level >= 2 ? &L.counters[IC_BACK + level] : nullptr, L.cap_rays, nf, n);
+    if (rederive) nf = n = L.n_slots;
+    if (level >= 2 && (long long)L.counters[level] + (long long)L.counters[IC_BACK + level] > (long long)L.cap_rays)
+        L.counters[IC_OVERFLOW] = 1;                           // the two ends met: the batch is re-run in halves
     if (level == 1 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&L.stats[ST_PRIMARY_RAYS], (unsigned long long)L.counters[1]);
     unsigned n_hit = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int i = queue_position(j, nf, L.cap_rays);
         const float4 h = q_load(&L.hits[i]);                // queues are streamed once: keep them out of the way of the BVH in L2
         const uint32_t prim1 = __float_as_uint(h.y);
         if (prim1 == 0u) continue;                          // miss: le(light, ray) == 0 (lights/light.jl:41)
@@ -201,8 +207,10 @@ __global__ void __launch_bounds__(128, TR_SHADE_MIN_BLOCKS) k_wh_shade(WhittedLa
                 const float adot = fabsf(dot3(bs.wi, it.ns));
                 if (!(bs.pdf > 0.0f && !is_black3(bs.f) && adot != 0.0f)) continue;
                 const float3 wn = w * (bs.f * adot / bs.pdf);
-                const int q = queue_claim(&L.counters[level + 1]);
-                if (q < L.cap_rays) {
+                // reflected rays fill the next level's queue from the front, transmitted rays from the back
+                const int k = queue_claim(&L.counters[(pass == 0 ? 0 : IC_BACK) + level + 1]);
+                const int q = pass == 0 ? k : L.cap_rays - 1 - k;
+                if (k < L.cap_rays) {
                     q_store(&L.ro[nxt][q], f4(it.p + 1e-6f * bs.wi, TR_INF));     // spawn_ray(si, wi), Trace.jl:206-211
                     q_store(&L.rd[nxt][q], f4(bs.wi, d4.w));
                     q_store(&L.rw[nxt][q], f4(wn, 0.0f));
@@ -385,7 +393,7 @@ __global__ void k_wh_batch_stats(int* counters, unsigned long long* stats, int m
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (batch_flag) *batch_flag = counters[IC_OVERFLOW];
         unsigned long long e = 0, s = 0;
-        for (int l = 1; l <= max_depth; ++l) e += min(counters[l], cap_rays);
+        for (int l = 1; l <= max_depth; ++l) e += min(counters[l] + (l >= 2 ? counters[IC_BACK + l] : 0), cap_rays);
         s = min(counters[32], cap_shadow);
         if (!counters[IC_OVERFLOW]) { atomicAdd(&stats[ST_RAYS_EXTEND], e); atomicAdd(&stats[ST_RAYS_SHADOW], s); }
     }
@@ -424,7 +432,7 @@ static int run_batch(trace_ctx* c, WhittedLaunch& L, long long begin, long long 
         c->cur_level = level;
         if (!(L.fused && level == 1))
             launch_extend(c, g_trav, L.sc, (const float4*)L.ro[cur], (const float4*)L.rd[cur], (const int*)(ic + level), L.cap_rays,
-                          L.hits, st + ST_NODES, d_err);
+                          L.hits, st + ST_NODES, d_err, level >= 2 ? (const int*)(ic + IC_BACK + level) : nullptr);
         c->kev_begin(TRACE_K_SHADE);
         k_wh_shade<<<occupancy_grid(c, k_wh_shade, 128), 128, 0, c->cur_stream>>>(L, level);
         c->kev_end();
