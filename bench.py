@@ -594,7 +594,8 @@ def bench_sppm(env, workload, steps, warmup, cpu_baseline=True):
         roofline["dram_frac"] = roofline["dram_achieved_GBps"] / peak
 
     # ---- e2e: trace_render_sppm, the call the Julia functor makes: n iterations + the image into a HOST buffer
-    n_it = int(min(p["iterations_per_render"], max(4, steps)))
+    # (iterations per render: the scene script's own count up to 25 - caustic_moving renders exactly its 25-iteration frame)
+    n_it = int(min(p["iterations_per_render"], 25))
     rgb = torch.zeros((h, w, 3), dtype=torch.float32).pin_memory()
 
     def render(i):
