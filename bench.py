@@ -693,7 +693,8 @@ def main():
         out = bench_whitted(env, args.workload)
         if not args.no_sppm:
             # the metric's second half: every SPPM workload as a complete line of its own (value, e2e, roofline, cpu_baseline)
-            out["sppm"] = [bench_sppm(env, wl, 10, 3, cpu_baseline=True) for wl in args.sppm_workloads.split(",") if wl]
+            # (30 iterations per timed call: with sppm_pipeline iterations in flight, fill and drain are part of the timed region)
+            out["sppm"] = [bench_sppm(env, wl, 30, 4, cpu_baseline=True) for wl in args.sppm_workloads.split(",") if wl]
             if env.world > 1:
                 out["sppm"].append({"sharded_vs_single_gpu_check": sppm_sharding_check(env)})
     if env.rank == 0:
