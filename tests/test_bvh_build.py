@@ -149,6 +149,39 @@ def test_optin_sah_tree_same_hits_less_work(T):
     assert float(b[3][0]) < 0.7 * float(a[3][0])                                 # fewer box tests (literal slab: 0.59x)
 
 
+def test_builder_signed_zeros_and_nan_bounds(T):
+    """Julia's min / max (NaN-propagating, -0.0 < +0.0) decide the bits of the node boxes; the product builder evaluates them
+    branch-free (MINSS(a, b) | MINSS(b, a)), the oracle with the branchy definition - boxes mixing +0.0 / -0.0 faces must
+    still give the same array bit for bit, in the sequential and in the parallel passes.  A NaN box has no bucket (the
+    reference's Int64(floor(NaN)) throws): the builder refuses it with an error code instead of building garbage."""
+    rng = np.random.default_rng(11)
+    for n in (300, 70_000):                                   # below / above the parallel top phase
+        b = random_bounds(rng, n)
+        z = rng.uniform(size=(n, 6)) < 0.15
+        b[z] = np.where(rng.uniform(size=int(z.sum())) < 0.5, np.float32(0.0), np.float32(-0.0))     # faces at +-0
+        lo, hi = np.minimum(b[:, :3], b[:, 3:]), np.maximum(b[:, :3], b[:, 3:])
+        b = np.concatenate([lo, hi], 1).astype(np.float32)
+        nodes, order = product_build(T, b)
+        rnodes, rorder, _ = oracle_lib.bvh_build(b)
+        assert len(nodes) == len(rnodes) and same(order, rorder)
+        assert np.array_equal(nodes["offset"], rnodes["offset"]) and np.array_equal(nodes["meta"], rnodes["meta"])
+        for f in ("bmin", "bmax"):
+            a, r = np.ascontiguousarray(nodes[f]), np.ascontiguousarray(rnodes[f])
+            assert np.array_equal(np.isnan(a), np.isnan(r))        # (a NaN's payload is not defined by min / max)
+            ok = ~np.isnan(a)
+            assert np.array_equal(a.view(np.uint32)[ok], r.view(np.uint32)[ok])      # bit patterns: -0.0 != +0.0
+
+
+def test_builder_refuses_nan_bounds(T):
+    import ctypes as C
+    from trace_jl_b200 import _lib as tl
+    lib = tl.load()
+    b = random_bounds(np.random.default_rng(2), 100)
+    b[17, 4] = np.nan
+    h = C.c_void_p()
+    assert lib.trace_bvh_build(tl.ptr(b), len(b), 1, C.byref(h)) != 0 and not h.value
+
+
 def test_threaded_build_is_bit_identical(T, monkeypatch):
     """The multi-threaded build (parallel passes over the large nodes + independent subtree jobs, then stitched into
     preorder) must produce the one-threaded array bit for bit - and that one equals the oracle's (the reference's split

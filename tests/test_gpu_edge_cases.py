@@ -118,6 +118,50 @@ def test_sppm_callback_cadence_and_default_photons(T, ctx):
     assert np.isfinite(rgb).all() and rgb.max() > 0
 
 
+def test_sppm_pipeline_depth_and_call_granularity_do_not_change_the_image(T):
+    """Iterations in flight (option sppm_pipeline: own visible-point arrays, queues and streams per slot; the camera pass no
+    longer reads the radius) and the way the iterations are handed over (one trace_sppm_iterate call with look-ahead, one
+    call per iteration, or the stepwise camera / grid / photon / update entry points) are scheduling only: after the same
+    iterations every variant must show the image of the strictly serial run, up to the order of the float flux atomics -
+    and that one is held to the oracle."""
+    from trace_jl_b200 import distributed as D
+    scene, camera, kw = T.scenes.shadows(resolution=96)
+    iters, r0, depth = 7, kw["initial_search_radius"], kw["max_depth"]
+
+    def run(pipeline, mode):
+        ctx = T.Context(0)
+        ctx.set_option("sppm_pipeline", pipeline)
+        flat = ctx.upload(scene)
+        sess = D.SPPMSession(ctx, scene, camera, r0, depth)
+        if mode == "one call":
+            sess.step(iters)
+        elif mode == "per iteration":
+            for _ in range(iters):
+                sess.step(1)
+        else:                                                  # stepwise entry points (slot 0 only)
+            photons = int(camera.film.crop_bounds.area())
+            for it in range(1, iters + 1):
+                ctx.check(ctx.lib.trace_sppm_camera_pass(ctx.h, it))
+                ctx.check(ctx.lib.trace_sppm_photon_pass(ctx.h, it, 0, photons))
+                ctx.check(ctx.lib.trace_sppm_update(ctx.h))
+            sess.iteration = iters
+        img = sess.image()
+        sess.close()
+        ctx.close()
+        return img, flat
+
+    base, flat = run(1, "one call")
+    assert np.isfinite(base).all() and base.max() > 0
+    for pipeline, mode in ((4, "one call"), (8, "one call"), (2, "per iteration"), (4, "per iteration"), (4, "stepwise")):
+        img, _ = run(pipeline, mode)
+        assert np.allclose(img, base, rtol=2e-4, atol=1e-6), (pipeline, mode, float(np.abs(img - base).max()))
+    cam, fd = camera.pod(), camera.film.desc()
+    ref = np.zeros_like(base)
+    oracle_lib.OracleScene(flat).render_sppm(cam, fd, r0, depth, iters, -1, 0x5EED0001, ref)
+    rel = float(np.mean((base - ref) ** 2) / max(1e-12, np.mean(ref ** 2)))
+    assert rel < 5e-3, rel
+
+
 def test_whitted_graph_replay_follows_seed_and_camera(T):
     """The render is captured once into a CUDA graph and replayed; seed and camera are read through a device block, so
     a replay with another seed / camera must give what direct launches give (bit for bit: same kernels, same order of

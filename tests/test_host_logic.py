@@ -209,3 +209,31 @@ def test_scale_and_mix_textures_fold_like_the_reference():
     # the material POD carries the folded value
     m = T.MatteMaterial(T.ScaleTexture(a, b), T.ConstantTexture(0.0))
     assert np.array_equal(np.asarray(m.pod()[1]), got)
+
+
+def test_grid_hash_magic_is_an_exact_modulo():
+    """sppm.cu:grid_hash replaces `h % n_pixels` (sppm.jl:497-501, UInt64) by q = mulhi64(h, magic) >> shift with
+    magic = ceil(2^(57 + L) / n), L = ceil(log2 n): exact for every h < 2^57 (cell coordinates are < 2^30, so the xor of
+    the three products stays below 2^57).  The same formula in Python integers, against `//` and `%`."""
+    import random
+    rng = random.Random(5)
+
+    def magic(n):
+        lg = 0
+        while (1 << lg) < n:
+            lg += 1
+        k = 57 + lg
+        return -(-(1 << k) // n), k
+
+    for n in [65, 100, 127, 128, 129, 96 * 96, 255 * 255, 1023 * 1023, 1024 * 1024, 1920 * 1080, 4096 * 4096, (1 << 31) - 1]:
+        m, k = magic(n)
+        assert m < (1 << 64) and k >= 64                       # fits the kernel's 64-bit magic and its `>> (k - 64)`
+        hs = [0, 1, n - 1, n, n + 1, (1 << 57) - 1, (1 << 57) - n, ((1 << 57) // n) * n, ((1 << 57) // n) * n - 1]
+        hs += [rng.getrandbits(57) for _ in range(20000)]
+        hs += [((x * 73856093) ^ (y * 19349663) ^ (z * 83492791)) for x, y, z in
+               ((rng.randrange(1 << 30), rng.randrange(1 << 30), rng.randrange(1 << 30)) for _ in range(20000))]
+        for h in hs:
+            if h >= (1 << 57):                                 # (n divides 2^57: outside the hash's range)
+                continue
+            q = ((h * m) >> 64) >> (k - 64)
+            assert q == h // n and h - q * n == h % n

@@ -546,14 +546,20 @@ int build_entry(const float* pb, int64_t n, int max_prims, trace_bvh** out) {
         const bool top_phase = build_threads() > 1 && n > 4096;      // scratch of the parallel partition
         std::unique_ptr<uint32_t[]> idx(top_phase ? new uint32_t[(size_t)n] : nullptr);
         std::unique_ptr<Rec[]> tmp(top_phase ? new Rec[(size_t)n] : nullptr);
+        std::atomic<int> bad(0);
         parallel_chunks(n, build_threads(), [&](int, int64_t b, int64_t e) {
             for (int64_t i = b; i < e; ++i) {
                 Rec& r = rec[(size_t)i];
                 r.id = (uint32_t)i;
                 for (int k = 0; k < 6; ++k) r.b[k] = pb[6 * i + k];
-                for (int k = 0; k < 3; ++k) r.c[k] = 0.5f * pb[6 * i + k] + 0.5f * pb[6 * i + 3 + k];
+                for (int k = 0; k < 3; ++k) {
+                    r.c[k] = 0.5f * pb[6 * i + k] + 0.5f * pb[6 * i + 3 + k];
+                    if (r.c[k] != r.c[k]) bad.store(1, std::memory_order_relaxed);
+                }
             }
         });
+        // a NaN centroid has no bucket: the reference's Int64(floor(NaN)) throws an InexactError (bvh.jl:118); refuse the input
+        if (bad.load()) { delete bvh; return 5; }
         Splitter split{rec.get(), max_prims, &pred, idx.get(), tmp.get()};
         const int rc = build_tree(split, rec.get(), n, bvh);
         if (rc) { delete bvh; return rc; }
