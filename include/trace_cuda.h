@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TRACE_ABI_VERSION 2
+#define TRACE_ABI_VERSION 3
 
 /* ---- BVH node, 32 bytes (LinearBVHLeaf / LinearBVHInterior, src/accel/bvh.jl:38-48) ----
  * interior: first child = self + 1, second child = `offset`; meta = split_axis << 30 (axis 0,1,2)

@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported(T):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/trace_cuda.h but not exported"
     assert set(syms) == set(tl.SIGNATURES), set(syms) ^ set(tl.SIGNATURES)
-    assert lib.trace_abi_version() == 2
+    assert lib.trace_abi_version() == 3
 
 
 def test_struct_layouts(T):

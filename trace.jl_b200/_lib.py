@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtrace_cuda.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 COMM_ID_BYTES = 128
 NODE_LEAF = 0xC0000000
 PRIM_TRIANGLE, PRIM_SPHERE = 0, 1
