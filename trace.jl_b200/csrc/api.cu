@@ -93,6 +93,7 @@ extern "C" void trace_destroy(trace_ctx* c) {
     for (DevBuf* b : all) b->release();
     for (auto& b : c->b_query) b.release();
     for (auto& b : c->b_queue) b.release();
+    c->p2p_film.release();
     for (auto& b : c->b_misc) b.release();
     for (auto& e : c->kev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int l = 0; l < trace_ctx::MAX_LANES; ++l) { if (c->side[l]) cudaStreamDestroy(c->side[l]); if (c->ev_join[l]) cudaEventDestroy(c->ev_join[l]); }
@@ -121,6 +122,7 @@ extern "C" int trace_set_option(trace_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "count_nodes")) c->count_nodes = v != 0;
     else if (!strcmp(key, "persist")) { if (v != 0) return c->fail("persist: the dynamic-ray-fetch kernels were measured slower in both rounds and removed (profiles/r2_experiments.md)"); }
     else if (!strcmp(key, "film_mode")) { if (v != 0 && v != 1) return c->fail("film_mode must be 0 (whole film on rank 0) or 1 (one band per rank)"); c->film_mode = (int)v; }
+    else if (!strcmp(key, "film_p2p")) { c->film_p2p = v != 0; }
     else if (!strcmp(key, "film_sum")) { if (v < 0 || v > 2) return c->fail("film_sum must be 0 (ncclReduce), 1 (ncclAllReduce) or 2 (reduce-scatter + gather)"); c->film_sum = (int)v; }
     else if (!strcmp(key, "sppm_path")) { if (v < 0 || v > TR_MAX_DEPTH) return c->fail("sppm_path must be in [0, %d]", TR_MAX_DEPTH); c->sppm_path = (int)v; }
     else if (!strcmp(key, "fuse_primary")) c->fuse_primary = v != 0;

@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include <cstring>
+#include <unistd.h>
 
 #include "context.hpp"
 
@@ -116,6 +117,7 @@ extern "C" int trace_comm_destroy(trace_ctx* c) {
     if (c->comm) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
+        comm_p2p_close(c);
         NcclApi* a = nccl_api();
         if (a->handle) a->CommDestroy((ncclComm_t)c->comm);
         c->comm = nullptr;
@@ -193,5 +195,73 @@ int comm_reduce_sum_via_scatter(trace_ctx* c, float* buf, size_t chunk, int root
     const ncclResult_t e = a->GroupEnd();
     if (r != ncclSuccess) return nccl_fail(c, "ncclSend / ncclRecv", r);
     if (e != ncclSuccess) return nccl_fail(c, "ncclGroupEnd", e);
+    return 0;
+}
+
+// ---- peer mappings of one device allocation per rank (the private films of a Whitted render)
+// Every rank publishes {IPC handle, raw pointer, pid, device} of `base` through an all-gather; a peer in ANOTHER process
+// is mapped with cudaIpcOpenMemHandle, a peer in THIS process (threads of one process, julia/TraceCUDA.jl MultiContext)
+// is used through its raw pointer after cudaDeviceEnablePeerAccess.  Collective; *all_ok = 1 only when every rank
+// mapped every peer (the ranks agree on it through a second tiny all-reduce), else the caller stays on NCCL.
+namespace {
+struct P2PInfo { cudaIpcMemHandle_t handle; unsigned long long ptr; long long pid; int device; int pad; };
+}
+void comm_p2p_close(trace_ctx* c) {
+    for (void* p : c->p2p_opened) cudaIpcCloseMemHandle(p);
+    c->p2p_opened.clear();
+    c->p2p_peer.clear();
+    c->p2p_state = 0;
+    c->p2p_npix = 0;
+}
+int comm_p2p_exchange(trace_ctx* c, void* base, std::vector<void*>& peers_out, std::vector<void*>& opened_out, int* all_ok) {
+    NcclApi* a = nccl_api();
+    *all_ok = 0;
+    if (!c->comm) return c->fail("no communicator: call trace_comm_init first");
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    const int world = c->world;
+    P2PInfo mine;
+    memset(&mine, 0, sizeof(mine));
+    int ok = cudaIpcGetMemHandle(&mine.handle, base) == cudaSuccess ? 1 : 0;
+    cudaGetLastError();
+    mine.ptr = (unsigned long long)(size_t)base; mine.pid = (long long)getpid(); mine.device = c->device;
+    char* d_buf = nullptr;
+    TR_CUDA(c, cudaMalloc((void**)&d_buf, (size_t)world * sizeof(P2PInfo) + 2 * sizeof(int)));
+    std::vector<P2PInfo> all((size_t)world);
+    TR_CUDA(c, cudaMemcpyAsync(d_buf + (size_t)c->rank * sizeof(P2PInfo), &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t r = a->AllGather(d_buf + (size_t)c->rank * sizeof(P2PInfo), d_buf, sizeof(P2PInfo), ncclChar, comm, c->stream);
+    if (r != ncclSuccess) { cudaFree(d_buf); return nccl_fail(c, "ncclAllGather (peer handles)", r); }
+    TR_CUDA(c, cudaMemcpyAsync(all.data(), d_buf, (size_t)world * sizeof(P2PInfo), cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    peers_out.assign((size_t)world, nullptr);
+    for (int p = 0; p < world && ok; ++p) {
+        if (p == c->rank) { peers_out[(size_t)p] = base; continue; }
+        if (all[(size_t)p].pid == mine.pid) {               // same process: the pointer is valid here, the device needs peer access
+            if (all[(size_t)p].device != c->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, c->device, all[(size_t)p].device);
+                if (!can) { ok = 0; break; }
+                const cudaError_t e = cudaDeviceEnablePeerAccess(all[(size_t)p].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                cudaGetLastError();
+            }
+            peers_out[(size_t)p] = (void*)(size_t)all[(size_t)p].ptr;
+        } else {
+            void* mapped = nullptr;
+            if (cudaIpcOpenMemHandle(&mapped, all[(size_t)p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+            opened_out.push_back(mapped);
+            peers_out[(size_t)p] = mapped;
+        }
+    }
+    // agreement: the number of ranks that failed, summed
+    int* d_fail = reinterpret_cast<int*>(d_buf + (size_t)world * sizeof(P2PInfo));
+    const int failed = ok ? 0 : 1;
+    int total = 1;
+    TR_CUDA(c, cudaMemcpyAsync(d_fail, &failed, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    r = a->AllReduce(d_fail, d_fail, 1, ncclInt, ncclSum, comm, c->stream);
+    if (r != ncclSuccess) { cudaFree(d_buf); return nccl_fail(c, "ncclAllReduce (peer mapping agreement)", r); }
+    TR_CUDA(c, cudaMemcpyAsync(&total, d_fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TR_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_buf);
+    *all_ok = total == 0 ? 1 : 0;
     return 0;
 }

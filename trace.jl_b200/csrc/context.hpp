@@ -87,6 +87,15 @@ struct trace_ctx {
     int rank = 0, world = 1;
     void* comm = nullptr;         // ncclComm_t of this rank (comm.cpp), null until trace_comm_init
     int nccl_version = 0;
+    // Peer-memory film sum (whitted.cu k_film_sum_p2p, comm.cpp comm_p2p_exchange): every rank's private film lives in an
+    // allocation the other ranks map (CUDA IPC between processes, plain peer access between threads of one process); the
+    // merge kernel of a rank then reads its band of ALL films over NVLink, sums and merges in one pass - no NCCL ring.
+    int film_p2p = 1;             // option: 0 = NCCL collectives only
+    DevBuf p2p_film;              // [private film | summed film (film_mode 0: the bands land in rank 0's)]
+    size_t p2p_npix = 0;          // padded pixel count the peers' mappings were exchanged for
+    int p2p_state = 0;            // 1 usable, -1 tried and failed on some rank (NCCL path), 0 not tried for this size
+    std::vector<void*> p2p_peer;  // rank r's p2p_film base in this process's address space
+    std::vector<void*> p2p_opened;   // IPC mappings to close
     int film_sum = 0;             // film_mode 0: 0 = ncclReduce to rank 0, 1 = ncclAllReduce, 2 = reduce-scatter + gather of the chunks onto rank 0
     int film_mode = 0;            // multi-rank Whitted film delivery: 0 = whole film summed onto rank 0, 1 = row bands (reduce-scatter)
     // CUDA graph of one Whitted render (all lanes, all batches): a render is ~20 launches per batch and the host
@@ -258,6 +267,8 @@ int comm_allreduce_sum(trace_ctx* ctx, float* buf, size_t count);
 int comm_allreduce_sum_int(trace_ctx* ctx, int* buf, size_t count);
 int comm_allgather(trace_ctx* ctx, const float* send, float* recv, size_t send_count);
 int comm_reduce_sum_via_scatter(trace_ctx* ctx, float* buf, size_t chunk, int root);
+int comm_p2p_exchange(trace_ctx* ctx, void* base, std::vector<void*>& peers_out, std::vector<void*>& opened_out, int* all_ok);
+void comm_p2p_close(trace_ctx* ctx);
 int comm_group_begin(trace_ctx* ctx);
 int comm_group_end(trace_ctx* ctx);
 // implemented in whitted.cu / sppm.cu

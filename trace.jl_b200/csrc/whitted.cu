@@ -379,6 +379,33 @@ __global__ void k_film_finalize(const float4* __restrict__ rgbw, float4* __restr
     }
 }
 
+// Film sum + merge over peer memory: ONE kernel instead of an NCCL collective followed by the merge.  peers.film[r] is
+// rank r's private film (mapped into this process, comm.cpp); this rank owns pixels [p0, p0 + n): it reads them from all
+// `world` films over NVLink (ld.cv: never from a stale L1 line), sums them in rank order (deterministic, unlike a ring) and
+// either merges the sum into the caller's film (film_mode 1: XYZ conversion + add, as k_film_finalize) or stores it into
+// rank 0's "summed film" region (film_mode 0: rank 0 merges the whole film after the closing barrier).
+struct FilmPeers { const float4* film[8]; float4* summed_on_root; };
+__global__ void __launch_bounds__(256) k_film_sum_p2p(FilmPeers peers, int world, long long p0, int n, float4* __restrict__ film /* caller's, or null */,
+                                                      const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const long long px = p0 + i;
+        float4 c = __ldcv(&peers.film[0][px]);
+        for (int r = 1; r < world; ++r) {
+            const float4 v = __ldcv(&peers.film[r][px]);
+            c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+        }
+        if (film) {
+            float4 f = film[px];
+            f.x += (0.412453f * c.x + 0.357580f * c.y) + 0.180423f * c.z;
+            f.y += (0.212671f * c.x + 0.715160f * c.y) + 0.072169f * c.z;
+            f.z += (0.019334f * c.x + 0.119193f * c.y) + 0.950227f * c.z;
+            f.w += c.w;
+            film[px] = f;
+        } else peers.summed_on_root[px] = c;
+    }
+}
+
 // any[0] = 1 when one of the render's batches overflowed or a traversal ran out of stack, any[1] = 1 for the latter alone
 // (with a communicator the pair is summed over the ranks, so that all of them take the same path afterwards)
 __global__ void k_wh_any_flag(const int* __restrict__ batch_flags, int n, const int* __restrict__ error_flag, int* __restrict__ any) {
@@ -552,8 +579,30 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     TR_CUDA(c, c->b_queue[11].ensure((size_t)K * batch * sizeof(float2)));
     const size_t npix = (size_t)L.film.width * L.film.height;
     const size_t npix_padded = (npix + (size_t)c->world - 1) / (size_t)c->world * (size_t)c->world;     // equal chunks for the reduce-scatter
-    TR_CUDA(c, c->b_queue[12].ensure(npix_padded * sizeof(float4)));
-    L.film_rgbw = c->b_queue[12].as<float4>();
+    // With a communicator of <= 8 ranks the private film lives in an allocation the other ranks map (peer-memory film
+    // sum, see k_film_sum_p2p): [private film | summed film].  The mappings are exchanged once per film size - a
+    // collective step, taken by all ranks in the same render because they all render the same film.
+    const bool want_p2p = c->comm != nullptr && c->world > 1 && c->world <= 8 && c->film_p2p;
+    if (want_p2p && (c->p2p_npix != npix_padded || c->p2p_state == 0)) {
+        TR_CUDA(c, cudaStreamSynchronize(c->stream));
+        comm_p2p_close(c);
+        c->p2p_film.release();
+        TR_CUDA(c, c->p2p_film.ensure(2 * npix_padded * sizeof(float4)));
+        int all_ok = 0;
+        if (comm_p2p_exchange(c, c->p2p_film.p, c->p2p_peer, c->p2p_opened, &all_ok)) return 1;
+        c->p2p_state = all_ok ? 1 : -1;
+        c->p2p_npix = npix_padded;
+        if (getenv("TRACE_CUDA_VERBOSE"))
+            fprintf(stderr, "[trace_cuda rank %d] peer-memory film sum %s (%d ranks, %zu film pixels)\n", c->rank,
+                    all_ok ? "enabled" : "unavailable: staying on NCCL", c->world, npix);
+        c->wh_graph_key.clear();
+    }
+    const bool p2p = want_p2p && c->p2p_state == 1;
+    if (p2p) L.film_rgbw = c->p2p_film.as<float4>();
+    else {
+        TR_CUDA(c, c->b_queue[12].ensure(npix_padded * sizeof(float4)));
+        L.film_rgbw = c->b_queue[12].as<float4>();
+    }
     L.stats = ctx_stats64(c);
     std::vector<WhittedLaunch> lane((size_t)K, L);
     for (int l = 0; l < K; ++l) {
@@ -567,7 +616,7 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
         W.accum = c->b_queue[10].as<float4>() + (size_t)l * batch; W.filmpos = c->b_queue[11].as<float2>() + (size_t)l * batch;
         W.counters = ctx_icounters_lane(c, l);
     }
-    TR_CUDA(c, c->b_misc[2].ensure((size_t)(nb + 2) * sizeof(int)));
+    TR_CUDA(c, c->b_misc[2].ensure((size_t)(nb + 4) * sizeof(int)));
     int* d_flags = c->b_misc[2].as<int>();
     TR_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     // everything up to the lanes' join: film clear, then batch bi on lane bi % K
@@ -631,6 +680,35 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     long long f0 = 0, f1 = (long long)npix;                     // film pixels this rank delivers
     whitted_film_range(c, (long long)npix, &f0, &f1);
     // The ONE exchange of a multi-rank render: the sum of the ranks' private films, on the render's stream.
+    // Peer-memory form: [barrier: every rank's private film is final] -> k_film_sum_p2p (sum + merge of this rank's pixels,
+    // read from all ranks' films) -> [barrier: nobody reads a private film any more, so the next render may clear it;
+    // film_mode 0: all bands have landed in rank 0's summed film] -> (film_mode 0, rank 0) merge of the whole film.  The
+    // barriers are one-int all-reduces; the first one is the flag all-reduce of the render when it directly precedes.
+    auto film_sum_p2p = [&](bool need_open_barrier, const int* skip) -> int {
+        TrRange nvtx_sum("whitted.film sum + merge (peer memory)");
+        c->kev_begin(TRACE_K_COMM);
+        int* d_bar = d_flags + nb + 2;
+        if (need_open_barrier && comm_allreduce_sum_int(c, d_bar, 1)) return 1;
+        FilmPeers peers;
+        for (int r = 0; r < 8; ++r) peers.film[r] = r < c->world ? reinterpret_cast<const float4*>(c->p2p_peer[(size_t)r]) : nullptr;
+        peers.summed_on_root = reinterpret_cast<float4*>(c->p2p_peer[0]) + npix_padded;
+        const size_t chunk = (npix + (size_t)c->world - 1) / (size_t)c->world;
+        const long long q0 = (long long)std::min(npix, (size_t)c->rank * chunk), q1 = (long long)std::min(npix, (size_t)(c->rank + 1) * chunk);
+        if (q1 > q0) {
+            if (c->film_mode == 1 && c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
+            k_film_sum_p2p<<<persistent_grid(c, 4), 256, 0, c->stream>>>(peers, c->world, q0, (int)(q1 - q0),
+                                                                         c->film_mode == 1 ? (float4*)film_dev : nullptr, skip);
+            c->stats.kernel_launches++;
+        }
+        if (comm_allreduce_sum_int(c, d_bar + 1, 1)) return 1;
+        c->kev_end();
+        if (c->film_mode == 0 && c->rank == 0) {
+            if (c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
+            k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(c->p2p_film.as<float4>() + npix_padded, (float4*)film_dev, (int)npix, skip);
+            c->stats.kernel_launches++;
+        }
+        return 0;
+    };
     auto film_sum = [&]() -> int {
         TrRange nvtx_sum("whitted.film sum (NCCL)");
         float* rgbw = reinterpret_cast<float*>(L.film_rgbw);
@@ -654,10 +732,12 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
     k_wh_any_flag<<<1, 32, 0, c->stream>>>(d_flags, (int)nb, d_err, d_flags + nb);
     c->stats.kernel_launches++;
     if (multi) {
+        TR_CUDA(c, cudaMemsetAsync(d_flags + nb + 2, 0, 2 * sizeof(int), c->stream));
         if (comm_allreduce_sum_int(c, d_flags + nb, 2)) return 1;          // every rank learns whether ANY rank has to redo batches
-        if (film_sum()) return 1;
+        if (p2p) { if (film_sum_p2p(false, d_flags + nb)) return 1; }      // (the flag all-reduce is the opening barrier)
+        else if (film_sum()) return 1;
     }
-    if (f1 > f0) {
+    if (f1 > f0 && !(multi && p2p)) {
         if (c->film_upload_pending) { TR_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0)); c->film_upload_pending = false; }
         k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw + f0, (float4*)film_dev + f0, (int)(f1 - f0), d_flags + nb);
         c->stats.kernel_launches++;
@@ -686,10 +766,13 @@ int whitted_render_device(trace_ctx* c, const trace_camera* cam, const trace_fil
             if (cnt < 2 * per_tile) return c->fail("ray queue overflow that halving the batch cannot resolve");
             if (run_batch(c, lane[0], b, half, 1) || run_batch(c, lane[0], b + half, cnt - half, 1)) return 1;
         }
-        if (multi && film_sum()) return 1;
-        if (f1 > f0) {
-            k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw + f0, (float4*)film_dev + f0, (int)(f1 - f0), nullptr);
-            c->stats.kernel_launches++;
+        if (multi && p2p) { if (film_sum_p2p(true, nullptr)) return 1; }
+        else {
+            if (multi && film_sum()) return 1;
+            if (f1 > f0) {
+                k_film_finalize<<<persistent_grid(c, 4), 256, 0, c->stream>>>(L.film_rgbw + f0, (float4*)film_dev + f0, (int)(f1 - f0), nullptr);
+                c->stats.kernel_launches++;
+            }
         }
         TR_CUDA(c, cudaEventRecord(c->ev1, c->stream));
         TR_CUDA(c, cudaStreamSynchronize(c->stream));
