@@ -177,7 +177,9 @@ const char* trace_last_error(const trace_ctx* ctx);
  *          their own streams and buffers while the serial chain grid -> deposits -> all-reduce -> update of the current
  *          one runs ("sppm_chain_priority" 0/1, default 1: that chain on a high-priority stream); "film_sum" how the
  *          whole film reaches rank 0 in film_mode 0: 0 ncclReduce, 1 ncclAllReduce, 2 reduce-scatter + gather of the
- *          chunks (default); "walk" traversal
+ *          chunks; "film_p2p" 0/1 (default 1): with a communicator of <= 8 ranks the film sum and the merge are one kernel
+ *          over peer memory (the ranks' private films mapped into every process), "film_sum" then only names the NCCL
+ *          fallback; "walk" traversal
  *          loop: 1 = pair nodes (default: one 64-byte fetch serves both children's box tests and the far child is
  *          pushed with its entry distance; same hits bit for bit), 0 = one node per step exactly as
  *          src/accel/bvh.jl:221-257; "leaf_wait" 0/4/8/16/32 warp-synchronous variant of loop 0 with batched leaf
