@@ -176,7 +176,7 @@ const char* trace_last_error(const trace_ctx* ctx);
  *          iterations in flight (1..8, default 4): the camera pass and the photon tracing of later iterations run on
  *          their own streams and buffers while the serial chain grid -> deposits -> all-reduce -> update of the current
  *          one runs ("sppm_chain_priority" 0/1, default 1: that chain on a high-priority stream); "film_sum" how the
- *          whole film reaches rank 0 in film_mode 0: 0 ncclReduce, 1 ncclAllReduce, 2 reduce-scatter + gather of the
+ *          whole film reaches rank 0 in film_mode 0: 0 ncclReduce (default), 1 ncclAllReduce, 2 reduce-scatter + gather of the
  *          chunks; "film_p2p" 0/1 (default 1): with a communicator of <= 8 ranks the film sum and the merge are one kernel
  *          over peer memory (the ranks' private films mapped into every process), "film_sum" then only names the NCCL
  *          fallback; "walk" traversal
