@@ -199,18 +199,32 @@ static void range_bounds(const Rec* rec, int64_t from, int64_t count, int parts,
     for (int p = 1; p < parts; ++p) { all.grow(pa[(size_t)p]); cb.grow(pc[(size_t)p]); }
 }
 
+// Top-phase plumbing of a split (large nodes, passes run in parallel): the node's records are read from `src`; when the
+// node is partitioned they are written - already permuted - into `dst` (the other one of the two record buffers), so no
+// copy-back pass is needed, and the pass that moves them also accumulates the two children's boxes, which the children
+// then take instead of a bounds pass of their own (min / max are exact and order-independent: same bits).
+struct TopIO {
+    const Rec* src; Rec* dst;
+    const Box* pre_all; const Box* pre_cb;      // this node's boxes when the parent computed them (else null)
+    bool moved = false;                          // the children's records live in dst
+    Box child_all[2], child_cb[2];               // valid when moved
+};
+
 struct LiteralSplitter {
+    static const bool kPingPong = true;
     Rec* rec; int max_prims;
     std::vector<uint8_t>* pred;        // scratch of the top phase (n entries each)
     uint32_t* idx; Rec* tmp;
     static const int NB = 12;
 
-    Split operator()(int64_t from, int64_t to, int threads) const {
+    Split operator()(int64_t from, int64_t to, int threads, TopIO* io = nullptr) const {
         Split r; r.leaf = false; r.axis = 0; r.mid = from;
         const int64_t count = to - from + 1;
         const int parts = (threads > 1 && count >= 32768) ? threads : 1;
+        Rec* const rec = io ? const_cast<Rec*>(io->src) : this->rec;      // (shadows the member: the node's records)
         Box all, cb;
-        range_bounds(rec, from, count, parts, all, cb);
+        if (io && io->pre_all) { all = *io->pre_all; cb = *io->pre_cb; }
+        else range_bounds(rec, from, count, parts, all, cb);
         for (int k = 0; k < 3; ++k) { r.node.bmin[k] = all.lo[k]; r.node.bmax[k] = all.hi[k]; }
         if (count == 1) { r.leaf = true; return r; }
         const int axis = cb.widest();
@@ -286,12 +300,34 @@ struct LiteralSplitter {
                 idx[left] = p ? a : b;
                 left += p;
             }
-            parallel_chunks(count, parts, [&](int, int64_t b, int64_t e) {
-                for (int64_t i = from + b; i < from + e; ++i) tmp[i] = rec[idx[i]];
-            });
-            parallel_chunks(count, parts, [&](int, int64_t b, int64_t e) {
-                memcpy(rec + from + b, tmp + from + b, (size_t)(e - b) * sizeof(Rec));
-            });
+            if (io) {
+                // one pass: permuted records into the other buffer + the children's boxes ([from, left] and (left, to])
+                Rec* const dst = io->dst;
+                std::vector<Box> pb((size_t)parts * 4);
+                parallel_chunks(count, parts, [&](int p, int64_t b, int64_t e) {
+                    Box* acc = &pb[(size_t)p * 4];
+                    for (int k = 0; k < 4; ++k) acc[k].reset();
+                    for (int64_t i = from + b; i < from + e; ++i) {
+                        const Rec v = rec[idx[i]];
+                        dst[i] = v;
+                        const int side = i <= left ? 0 : 1;
+                        acc[2 * side].grow(v.b, v.b + 3);
+                        acc[2 * side + 1].grow(v.c, v.c);
+                    }
+                });
+                for (int side = 0; side < 2; ++side) {
+                    io->child_all[side] = pb[(size_t)2 * side]; io->child_cb[side] = pb[(size_t)2 * side + 1];
+                    for (int p = 1; p < parts; ++p) { io->child_all[side].grow(pb[(size_t)p * 4 + 2 * side]); io->child_cb[side].grow(pb[(size_t)p * 4 + 2 * side + 1]); }
+                }
+                io->moved = true;
+            } else {
+                parallel_chunks(count, parts, [&](int, int64_t b, int64_t e) {
+                    for (int64_t i = from + b; i < from + e; ++i) tmp[i] = rec[idx[i]];
+                });
+                parallel_chunks(count, parts, [&](int, int64_t b, int64_t e) {
+                    memcpy(rec + from + b, tmp + from + b, (size_t)(e - b) * sizeof(Rec));
+                });
+            }
         } else {
             for (int64_t i = from; i <= to; ++i)
                 if (left != i && bucket(rec[i]) <= best) { std::swap(rec[i], rec[left]); ++left; }
@@ -305,12 +341,13 @@ struct LiteralSplitter {
 // COUNT (cost = 1/8 + (nL*aL + nR*aR)/A), a node becomes a leaf when that is cheaper and it holds <=
 // max_node_primitives, the partition tests every element, and a degenerate split falls back to the median.
 struct SahSplitter {
+    static const bool kPingPong = false;
     Rec* rec; int max_prims;
     std::vector<uint8_t>* pred;
     uint32_t* idx; Rec* tmp;
     static const int NB = 16;
 
-    Split operator()(int64_t from, int64_t to, int threads) const {
+    Split operator()(int64_t from, int64_t to, int threads, TopIO* = nullptr) const {
         Split r; r.leaf = false; r.axis = 0;
         const int64_t count = to - from + 1;
         const int parts = (threads > 1 && count >= 32768) ? threads : 1;
@@ -437,12 +474,17 @@ int build_tree(Splitter split, const Rec* rec, int64_t n, trace_bvh* bvh) {
     const double t_begin = now_s();
     // ~16 jobs per thread (subtree sizes vary a lot: the literal tree is unbalanced), never below 4096 primitives
     const int64_t job_threshold = std::max<int64_t>(4096, std::min<int64_t>(kTopThreshold, n / (16 * (int64_t)threads)));
-    struct Item { int kind; trace_bvh_node node; int64_t from, to; int64_t second_item; int job; };   // kind 0 interior, 1 leaf, 2 job
+    struct Item { int kind; trace_bvh_node node; int64_t from, to; int64_t second_item; int job; const Rec* base; };   // kind 0 interior, 1 leaf, 2 job
     std::vector<Item> items;
-    std::vector<std::pair<int64_t, int64_t>> jobs;
-    struct TopTask { int64_t from, to; int64_t patch_item; };
+    struct Job { int64_t from, to; Rec* base; };
+    std::vector<Job> jobs;
+    // `base`: which of the two record buffers holds the task's range (a partitioned top-phase node writes its children
+    // into the other one); `boxes`: the parent computed this node's boxes while moving the records
+    struct TopTask { int64_t from, to; int64_t patch_item; Rec* base; bool boxes; Box all, cb; };
     std::vector<TopTask> todo;
-    todo.push_back({0, n - 1, -1});
+    Rec* const buf0 = const_cast<Rec*>(rec);
+    Rec* const buf1 = split.tmp;
+    { TopTask root; root.from = 0; root.to = n - 1; root.patch_item = -1; root.base = buf0; root.boxes = false; todo.push_back(root); }
     while (!todo.empty()) {
         const TopTask t = todo.back();
         todo.pop_back();
@@ -450,24 +492,34 @@ int build_tree(Splitter split, const Rec* rec, int64_t n, trace_bvh* bvh) {
         if (t.patch_item >= 0) items[(size_t)t.patch_item].second_item = me;
         const int64_t count = t.to - t.from + 1;
         if (threads == 1 ? false : count <= job_threshold) {
-            items.push_back({2, trace_bvh_node(), t.from, t.to, -1, (int)jobs.size()});
-            jobs.push_back({t.from, t.to});
+            items.push_back({2, trace_bvh_node(), t.from, t.to, -1, (int)jobs.size(), t.base});
+            jobs.push_back({t.from, t.to, t.base});
             continue;
         }
         if (threads == 1 && me == 0) {          // one thread: the plain sequential build of the whole range
-            items.push_back({2, trace_bvh_node(), t.from, t.to, -1, 0});
-            jobs.push_back({t.from, t.to});
+            items.push_back({2, trace_bvh_node(), t.from, t.to, -1, 0, t.base});
+            jobs.push_back({t.from, t.to, t.base});
             continue;
         }
-        Split s = split(t.from, t.to, threads);
+        TopIO io;
+        io.src = t.base; io.dst = t.base == buf0 ? buf1 : buf0;
+        io.pre_all = t.boxes ? &t.all : nullptr; io.pre_cb = t.boxes ? &t.cb : nullptr;
+        const bool ping_pong = Splitter::kPingPong && buf1 != nullptr;
+        Split s = split(t.from, t.to, threads, ping_pong ? &io : nullptr);
         if (s.leaf) {
             s.node.meta = TRACE_NODE_LEAF | (uint32_t)count;
-            items.push_back({1, s.node, t.from, t.to, -1, -1});
+            items.push_back({1, s.node, t.from, t.to, -1, -1, t.base});
         } else {
             s.node.meta = (uint32_t)s.axis << 30;
-            items.push_back({0, s.node, t.from, t.to, -1, -1});
-            todo.push_back({s.mid + 1, t.to, me});
-            todo.push_back({t.from, s.mid, -1});
+            items.push_back({0, s.node, t.from, t.to, -1, -1, t.base});
+            const bool moved = ping_pong && io.moved;
+            Rec* const child_base = moved ? io.dst : t.base;
+            TopTask second, first;
+            second.from = s.mid + 1; second.to = t.to; second.patch_item = me; second.base = child_base; second.boxes = moved;
+            first.from = t.from; first.to = s.mid; first.patch_item = -1; first.base = child_base; first.boxes = moved;
+            if (moved) { first.all = io.child_all[0]; first.cb = io.child_cb[0]; second.all = io.child_all[1]; second.cb = io.child_cb[1]; }
+            todo.push_back(second);
+            todo.push_back(first);
         }
     }
     const double t_top = now_s();
@@ -479,10 +531,12 @@ int build_tree(Splitter split, const Rec* rec, int64_t n, trace_bvh* bvh) {
             for (;;) {
                 const size_t j = next.fetch_add(1);
                 if (j >= jobs.size()) break;
-                const int64_t cnt = jobs[j].second - jobs[j].first + 1;
+                const int64_t cnt = jobs[j].to - jobs[j].from + 1;
                 local[j].nodes.reserve((size_t)(2 * cnt + 16));
                 local[j].order.reserve((size_t)cnt);
-                rcs[j] = build_subtree(split, rec, jobs[j].first, jobs[j].second, local[j]);
+                Splitter mine = split;                       // the job's records may live in either buffer
+                mine.rec = jobs[j].base;
+                rcs[j] = build_subtree(mine, jobs[j].base, jobs[j].from, jobs[j].to, local[j]);
             }
         };
         const int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, jobs.size()));
@@ -514,7 +568,7 @@ int build_tree(Splitter split, const Rec* rec, int64_t n, trace_bvh* bvh) {
                 trace_bvh_node nd = it.node;
                 nd.offset = (uint32_t)order_base[(size_t)i];
                 bvh->nodes[(size_t)node_base[(size_t)i]] = nd;
-                for (int64_t k = it.from; k <= it.to; ++k) bvh->order[(size_t)(order_base[(size_t)i] + k - it.from)] = rec[k].id;
+                for (int64_t k = it.from; k <= it.to; ++k) bvh->order[(size_t)(order_base[(size_t)i] + k - it.from)] = it.base[k].id;
             } else {
                 const LocalTree& lt = local[(size_t)it.job];
                 const uint32_t nb = (uint32_t)node_base[(size_t)i], ob = (uint32_t)order_base[(size_t)i];
