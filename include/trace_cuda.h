@@ -149,7 +149,9 @@ typedef struct trace_stats {
 typedef struct trace_ctx trace_ctx;
 typedef struct trace_bvh trace_bvh;
 
-/* ---- host-side BVH build, no GPU needed ---- */
+/* ---- host-side BVH build, no GPU needed (multi-threaded: TRACE_BVH_THREADS, default all cores; the tree does not depend on
+ * the thread count).  Return codes: 0 ok, 1 bad argument, 2 out of memory, 3 / 4 node count out of range, 5 a primitive
+ * bound is NaN (the reference's Int64(floor(NaN)) throws an InexactError there, src/accel/bvh.jl:118) ---- */
 int     trace_bvh_build(const float* prim_bounds /* [n][6] = min xyz, max xyz */, int64_t n,
                         int max_node_primitives, trace_bvh** out);
 /* opt-in: conventional binned SAH (primitive-count weighted, empty buckets, leaves up to max_node_primitives) in the same
